@@ -1,0 +1,364 @@
+// D3PM forward noising (row Q) and closed-form reverse step (row P), SURVEY.md §8(a).
+// One warp per token, O(K) work, fp32 in registers; the reference's dense (K,K) fp16 matmuls
+// (ar_discrete.py:337-345,377-400) collapse to a handful of per-timestep scalars.
+#include "common.cuh"
+
+namespace vb200 {
+
+constexpr float kEps = 1.0e-6f;          // ar_discrete.py:276
+constexpr float kTiny = 1.17549435e-38f; // torch.finfo(float32).tiny, ar_discrete.py:414,485
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      c0 = hi1 ^ c1 ^ a;
+      c1 = lo1;
+      c2 = hi0 ^ c3 ^ b;
+      c3 = lo0;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+__device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * 5.9604644775390625e-8f; }
+
+// Gumbel noise exactly as the reference forms it, evaluated through double so that each fp32
+// log is correctly rounded (the CPU reference's SLEEF logf is <= 1 ulp; agreeing with the
+// correctly rounded value is the closest a different libm can get).
+__device__ __forceinline__ float gumbel_exact(float u) {
+  u = fminf(fmaxf(u, kTiny), 1.0f);
+  const float inner = static_cast<float>(log(static_cast<double>(u)));
+  return -static_cast<float>(log(static_cast<double>(-inner)));
+}
+__device__ __forceinline__ float gumbel_fast(float u) {
+  u = fmaxf(u, kTiny);
+  return -__logf(-__logf(u));
+}
+
+struct Best {
+  float v;
+  int j;
+};
+__device__ __forceinline__ void best_update(Best& b, float v, int j) {
+  if (v > b.v || (v == b.v && j < b.j)) { b.v = v; b.j = j; }
+}
+__device__ __forceinline__ Best warp_best(Best b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v = __shfl_xor_sync(0xffffffffu, b.v, o);
+    const int j = __shfl_xor_sync(0xffffffffu, b.j, o);
+    best_update(b, v, j);
+  }
+  return b;
+}
+
+// ---------------------------------------------------------------- Q: q_sample
+__global__ void __launch_bounds__(256) q_sample_kernel(
+    int32_t* __restrict__ x_out, const int32_t* __restrict__ x0, const int32_t* __restrict__ t_tok,
+    const int32_t* __restrict__ mask, const float* __restrict__ uniforms,
+    const float* __restrict__ table, int n_tok, int K, int S, int transition) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int tok = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tok < n_tok;
+       tok += gridDim.x * warps_per_block) {
+    const int x = x0[tok];
+    int t = t_tok[tok];
+    t = min(max(t, 0), S - 1);
+    const float* tab = table + static_cast<size_t>(t) * VB200_TAB_STRIDE;
+    const int m = K / 2;
+    const bool absorbing = transition == VB200_ABSORBING;
+    const float l_keep = tab[VB200_TAB_LOG_KEEP], l_off = tab[VB200_TAB_LOG_OFF];
+    const float l_abs = tab[VB200_TAB_LOG_ABSORB], l_both = tab[VB200_TAB_LOG_BOTH];
+    const float* u = uniforms + static_cast<size_t>(tok) * K;
+    Best best{-INFINITY, 0x7fffffff};
+    for (int j = lane; j < K; j += 32) {
+      float lg;
+      if (absorbing) {
+        if (x == m) lg = (j == m) ? l_both : l_off;           // row m of Qbar: [0 .. 1 .. 0]
+        else lg = (j == x) ? l_keep : ((j == m) ? l_abs : l_off);
+      } else {
+        lg = (j == x) ? l_keep : l_off;
+      }
+      best_update(best, lg + gumbel_exact(__ldg(u + j)), j);
+    }
+    best = warp_best(best);
+    if (lane == 0) x_out[tok] = best.j * (mask ? mask[tok] : 1);
+  }
+}
+
+// ---------------------------------------------------------------- P: posterior + sample
+template <typename T>
+__device__ __forceinline__ float load_logit(const T* p, int j);
+template <>
+__device__ __forceinline__ float load_logit<float>(const float* p, int j) { return __ldg(p + j); }
+template <>
+__device__ __forceinline__ float load_logit<__nv_bfloat16>(const __nv_bfloat16* p, int j) {
+  return __bfloat162float(p[j]);
+}
+template <>
+__device__ __forceinline__ float load_logit<__half>(const __half* p, int j) {
+  return __half2float(p[j]);
+}
+
+// Loads 8 consecutive logits (16-byte aligned for 2-byte types) into fp32.
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <>
+__device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <>
+__device__ __forceinline__ void load8<__half>(const __half* p, float (&v)[8]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+
+struct PostConst {
+  float f1_self, f1_oth;      // Q_t[j, x_t] for j == x_t / j != x_t
+  float a_gen, c_gen;         // f2_j = p_j * a + (1 - p_j) * c for generic j
+  float a_m, c_m;             // ... for j == m (absorbing only; equals generic for uniform)
+  int x_t, m;
+  bool raw;                   // t == 0: posterior logits are the raw logits (ar_discrete.py:374,407)
+};
+
+__device__ __forceinline__ float post_logit(const PostConst& pc, float logit, float p, int j) {
+  if (pc.raw) return logit;
+  const float f1 = (j == pc.x_t) ? pc.f1_self : pc.f1_oth;
+  const bool is_m = (j == pc.m);
+  const float a = is_m ? pc.a_m : pc.a_gen, c = is_m ? pc.c_m : pc.c_gen;
+  const float f2 = fmaf(p, a - c, c);
+  return logf(f1 + kEps) + logf(f2 + kEps);
+}
+
+template <typename T, int NOISE>
+__global__ void __launch_bounds__(256) posterior_sample_kernel(
+    int32_t* __restrict__ x_out, float* __restrict__ post_out, const T* __restrict__ logits,
+    int64_t ld_logits, const int32_t* __restrict__ x_t_all, const int32_t* __restrict__ row_utt,
+    const int32_t* __restrict__ t_utt, const int32_t* __restrict__ utt,
+    const float* __restrict__ table, int n_rows, int n_levels, int K, int S, int transition,
+    const float* __restrict__ uniforms, uint32_t seed_lo, uint32_t seed_hi) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tok = n_rows * n_levels;
+  const bool vec = (K % 8 == 0) && (ld_logits % 8 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  for (int tok = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tok < n_tok;
+       tok += gridDim.x * warps_per_block) {
+    const int row = tok / n_levels, level = tok - row * n_levels;
+    const int b = row_utt[row];
+    const int t = min(max(t_utt[b], 0), S - 1);
+    const int t1 = t > 0 ? t - 1 : 0;
+    const float* one = table + static_cast<size_t>(t) * VB200_TAB_STRIDE;
+    const float* cum = table + static_cast<size_t>(t1) * VB200_TAB_STRIDE;
+    PostConst pc;
+    pc.x_t = x_t_all[tok];
+    pc.m = (transition == VB200_ABSORBING) ? K / 2 : -1;
+    pc.raw = (t == 0);
+    if (transition == VB200_ABSORBING) {
+      const bool at_m = pc.x_t == pc.m;
+      pc.f1_self = at_m ? one[VB200_TAB_ONE_BOTH] : one[VB200_TAB_ONE_KEEP];
+      pc.f1_oth = at_m ? one[VB200_TAB_ONE_ABSORB] : one[VB200_TAB_ONE_OFF];
+      pc.a_gen = cum[VB200_TAB_CUM_KEEP]; pc.c_gen = cum[VB200_TAB_CUM_OFF];
+      pc.a_m = cum[VB200_TAB_CUM_BOTH];   pc.c_m = cum[VB200_TAB_CUM_ABSORB];
+    } else {
+      pc.f1_self = one[VB200_TAB_ONE_KEEP]; pc.f1_oth = one[VB200_TAB_ONE_OFF];
+      pc.a_gen = pc.a_m = cum[VB200_TAB_CUM_KEEP];
+      pc.c_gen = pc.c_m = cum[VB200_TAB_CUM_OFF];
+    }
+    const T* lrow = logits + static_cast<size_t>(row) * ld_logits + static_cast<size_t>(level) * K;
+
+    // pass 1: row max; pass 2: sum exp (the row is 2-4 KB and stays in L1 between passes)
+    float mx = -INFINITY;
+    if (vec) {
+      for (int j0 = lane * 8; j0 < K; j0 += 256) {
+        float v[8]; load8<T>(lrow + j0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mx = fmaxf(mx, v[i]);
+      }
+    } else {
+      for (int j = lane; j < K; j += 32) mx = fmaxf(mx, load_logit<T>(lrow, j));
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    if (vec) {
+      for (int j0 = lane * 8; j0 < K; j0 += 256) {
+        float v[8]; load8<T>(lrow + j0, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum += __expf(v[i] - mx);
+      }
+    } else {
+      for (int j = lane; j < K; j += 32) sum += __expf(load_logit<T>(lrow, j) - mx);
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+
+    // Philox key: (seed) ; counter: (j/4, frame*n_levels+level, global utterance id, t)
+    uint32_t gid = 0, frame = 0;
+    if (NOISE == VB200_NOISE_PHILOX) {
+      const int32_t* ur = utt + static_cast<size_t>(b) * VB200_U_STRIDE;
+      gid = static_cast<uint32_t>(ur[VB200_U_GID]);
+      frame = static_cast<uint32_t>(row - ur[VB200_U_RESP0]);
+    }
+    const Philox ph{seed_lo, seed_hi};
+    const float* urow = (NOISE == VB200_NOISE_UNIFORMS) ? uniforms + static_cast<size_t>(tok) * K : nullptr;
+    float* prow = post_out ? post_out + static_cast<size_t>(tok) * K : nullptr;
+    const bool noisy = !pc.raw;   // nonzero_mask, ar_discrete.py:412-419
+
+    Best best{-INFINITY, 0x7fffffff};
+    if (vec) {
+      for (int j0 = lane * 8; j0 < K; j0 += 256) {
+        float v[8]; load8<T>(lrow + j0, v);
+        float g[8];
+        if (NOISE == VB200_NOISE_PHILOX) {
+          const uint4 r0 = ph(j0 >> 2, frame * n_levels + level, gid, t);
+          const uint4 r1 = ph((j0 >> 2) + 1, frame * n_levels + level, gid, t);
+          const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = gumbel_fast(u01(rr[i]));
+        } else if (NOISE == VB200_NOISE_UNIFORMS) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = gumbel_exact(__ldg(urow + j0 + i));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = j0 + i;
+          const float pl = post_logit(pc, v[i], __expf(v[i] - mx) * inv, j);
+          if (prow) prow[j] = pl;
+          const float sc = (NOISE != VB200_NOISE_GREEDY && noisy) ? pl + g[i] : pl;
+          best_update(best, sc, j);
+        }
+      }
+    } else {
+      for (int j = lane; j < K; j += 32) {
+        const float l = load_logit<T>(lrow, j);
+        const float pl = post_logit(pc, l, __expf(l - mx) * inv, j);
+        if (prow) prow[j] = pl;
+        float sc = pl;
+        if (NOISE == VB200_NOISE_PHILOX && noisy) {
+          const uint4 r = ph(j >> 2, frame * n_levels + level, gid, t);
+          const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+          sc += gumbel_fast(u01(rr[j & 3]));
+        } else if (NOISE == VB200_NOISE_UNIFORMS && noisy) {
+          sc += gumbel_exact(__ldg(urow + j));
+        }
+        best_update(best, sc, j);
+      }
+    }
+    best = warp_best(best);
+    if (lane == 0) x_out[tok] = best.j;
+  }
+}
+
+template <typename T>
+static int launch_posterior(int32_t* x_out, float* post_out, const void* logits, int64_t ld,
+                            const int32_t* x_t, const int32_t* row_utt, const int32_t* t_utt,
+                            const int32_t* utt, const float* table, int n_rows, int n_levels,
+                            int K, int S, int tr, int noise, const float* uniforms,
+                            uint64_t seed, cudaStream_t st) {
+  const int n_tok = n_rows * n_levels;
+  const int wpb = 8;
+  int grid = (n_tok + wpb - 1) / wpb;
+  const int cap = num_sms() * 8 * 4;
+  if (grid > cap) grid = cap;
+  const uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
+#define VB_LAUNCH_P(NZ)                                                                        \
+  posterior_sample_kernel<T, NZ><<<grid, wpb * 32, 0, st>>>(                                   \
+      x_out, post_out, static_cast<const T*>(logits), ld, x_t, row_utt, t_utt, utt, table,     \
+      n_rows, n_levels, K, S, tr, uniforms, lo, hi)
+  if (noise == VB200_NOISE_PHILOX) VB_LAUNCH_P(VB200_NOISE_PHILOX);
+  else if (noise == VB200_NOISE_UNIFORMS) VB_LAUNCH_P(VB200_NOISE_UNIFORMS);
+  else VB_LAUNCH_P(VB200_NOISE_GREEDY);
+#undef VB_LAUNCH_P
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
+}
+
+__global__ void step_timesteps_kernel(int32_t* t_utt, int B, int delta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) t_utt[i] += delta;
+}
+
+}  // namespace vb200
+
+using namespace vb200;
+
+extern "C" int vb200_q_sample(int32_t* x_out, const int32_t* x0, const int32_t* t_tok,
+                              const int32_t* mask, const float* uniforms, const float* table,
+                              int32_t n_tok, int32_t K, int32_t S, vb200_transition tr,
+                              vb200_stream_t stream) {
+  VB_REQUIRE(x_out && x0 && t_tok && uniforms && table, "q_sample: null pointer");
+  VB_REQUIRE(n_tok >= 0 && K >= 2 && S >= 1, "q_sample: bad sizes n_tok=%d K=%d S=%d", n_tok, K, S);
+  if (n_tok == 0) return VB200_OK;
+  const int wpb = 8;
+  int grid = (n_tok + wpb - 1) / wpb;
+  const int cap = num_sms() * 32;
+  if (grid > cap) grid = cap;
+  q_sample_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_out, x0, t_tok, mask, uniforms, table, n_tok, K, S, static_cast<int>(tr));
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
+}
+
+extern "C" int vb200_posterior_sample_from_logits(
+    int32_t* x_out, float* post_out, const void* logits, vb200_dtype logits_dtype,
+    int64_t ld_logits, const int32_t* x_t, const int32_t* row_utt, const int32_t* t_utt,
+    const int32_t* utt, const float* table, int32_t n_rows, int32_t n_levels, int32_t K,
+    int32_t S, vb200_transition tr, vb200_noise noise, const float* uniforms, uint64_t seed,
+    vb200_stream_t stream) {
+  VB_REQUIRE(x_out && logits && x_t && row_utt && t_utt && table, "posterior: null pointer");
+  VB_REQUIRE(n_rows >= 0 && n_levels >= 1 && K >= 2 && S >= 1, "posterior: bad sizes");
+  VB_REQUIRE(ld_logits >= static_cast<int64_t>(n_levels) * K, "posterior: ld_logits too small");
+  VB_REQUIRE(noise != VB200_NOISE_UNIFORMS || uniforms, "posterior: uniforms required");
+  VB_REQUIRE(noise != VB200_NOISE_PHILOX || utt, "posterior: utt records required for Philox");
+  if (n_rows == 0) return VB200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (logits_dtype) {
+    case VB200_F32:
+      return launch_posterior<float>(x_out, post_out, logits, ld_logits, x_t, row_utt, t_utt, utt,
+                                     table, n_rows, n_levels, K, S, tr, noise, uniforms, seed, st);
+    case VB200_BF16:
+      return launch_posterior<__nv_bfloat16>(x_out, post_out, logits, ld_logits, x_t, row_utt,
+                                             t_utt, utt, table, n_rows, n_levels, K, S, tr, noise,
+                                             uniforms, seed, st);
+    case VB200_F16:
+      return launch_posterior<__half>(x_out, post_out, logits, ld_logits, x_t, row_utt, t_utt,
+                                      utt, table, n_rows, n_levels, K, S, tr, noise, uniforms,
+                                      seed, st);
+  }
+  set_error("posterior: unknown logits dtype %d", static_cast<int>(logits_dtype));
+  return VB200_ERR_INVALID;
+}
+
+extern "C" int vb200_step_timesteps(int32_t* t_utt, int32_t B, int32_t delta,
+                                    vb200_stream_t stream) {
+  VB_REQUIRE(t_utt && B >= 0, "step_timesteps: bad arguments");
+  if (B == 0) return VB200_OK;
+  step_timesteps_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t_utt, B, delta);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
+}

@@ -1,0 +1,232 @@
+// HBM-bound kernels of the denoiser: embedding gather-sum (rows E1-E4, T), AdaLN / LayerNorm
+// (rows N1, N2) and the response-row gather in front of the classifier (row H1).
+// One warp per row; 16-byte vector accesses; fp32 math.
+#include "common.cuh"
+
+namespace vb200 {
+
+__device__ __forceinline__ void add_bf16x8(float (&acc)[8], const __nv_bfloat16* p) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    acc[2 * i] += __uint_as_float(w[i] << 16);
+    acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+
+// x[r] = emb(row r) + pe[pos]   (base.py:427-436)
+__global__ void __launch_bounds__(256) embed_gather_kernel(
+    float* __restrict__ x_out, const __nv_bfloat16* __restrict__ text_w,
+    const __nv_bfloat16* __restrict__ prom_w, const __nv_bfloat16* __restrict__ resp_w,
+    const __nv_bfloat16* __restrict__ sep, const __nv_bfloat16* __restrict__ time_w,
+    const float* __restrict__ pe, const int32_t* __restrict__ text_ids,
+    const int32_t* __restrict__ prom_ids, const int32_t* __restrict__ resp_ids,
+    const int32_t* __restrict__ utt, const int32_t* __restrict__ row_utt,
+    const int32_t* __restrict__ t_utt, int M, int d, int K, int resp_levels_in) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
+    const int b = row_utt[r];
+    const int32_t* u = utt + static_cast<size_t>(b) * VB200_U_STRIDE;
+    const int pos = r - u[VB200_U_ROW0];
+    const int t_txt = u[VB200_U_TTXT], t_prom = u[VB200_U_TPROM];
+    // segment: [text][sep][prom][sep][resp]
+    int kind, idx;
+    if (pos < t_txt) { kind = 0; idx = pos; }
+    else if (pos == t_txt) { kind = 1; idx = 0; }
+    else if (pos < t_txt + 1 + t_prom) { kind = 2; idx = pos - t_txt - 1; }
+    else if (pos == t_txt + 1 + t_prom) { kind = 1; idx = 0; }
+    else { kind = 3; idx = pos - t_txt - t_prom - 2; }
+
+    const __nv_bfloat16* rows[9];
+    int n_rows = 0;
+    if (kind == 0) {
+      rows[n_rows++] = text_w + static_cast<size_t>(text_ids[u[VB200_U_TXT0] + idx]) * d;
+    } else if (kind == 1) {
+      rows[n_rows++] = sep;
+    } else if (kind == 2) {
+      const int32_t* ids = prom_ids + static_cast<size_t>(u[VB200_U_PROM0] + idx) * 8;
+#pragma unroll
+      for (int l = 0; l < 8; ++l)
+        rows[n_rows++] = prom_w + (static_cast<size_t>(l) * K + ids[l]) * d;
+    } else {
+      const int32_t* ids = resp_ids + static_cast<size_t>(u[VB200_U_RESP0] + idx) * resp_levels_in;
+      for (int l = 0; l < resp_levels_in; ++l)
+        rows[n_rows++] = resp_w + (static_cast<size_t>(l) * K + ids[l]) * d;
+      if (time_w) rows[n_rows++] = time_w + static_cast<size_t>(t_utt[b]) * d;
+    }
+    const float* pe_row = pe + static_cast<size_t>(pos) * d;
+    float* out = x_out + static_cast<size_t>(r) * d;
+    for (int c = lane * 8; c < d; c += 256) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < n_rows; ++i) add_bf16x8(acc, rows[i] + c);
+      const float4 p0 = __ldg(reinterpret_cast<const float4*>(pe_row + c));
+      const float4 p1 = __ldg(reinterpret_cast<const float4*>(pe_row + c) + 1);
+      float4 o0 = make_float4(acc[0] + p0.x, acc[1] + p0.y, acc[2] + p0.z, acc[3] + p0.w);
+      float4 o1 = make_float4(acc[4] + p1.x, acc[5] + p1.y, acc[6] + p1.z, acc[7] + p1.w);
+      reinterpret_cast<float4*>(out + c)[0] = o0;
+      reinterpret_cast<float4*>(out + c)[1] = o1;
+    }
+  }
+}
+
+// Row statistics + normalisation.  MODE 0: AdaLN (base.py:145-158), MODE 1: affine LayerNorm.
+// d <= 32 * 8 * MAXV elements are kept in registers between the two passes.
+template <int MODE>
+__global__ void __launch_bounds__(256) norm_kernel(
+    __nv_bfloat16* __restrict__ out, const float* __restrict__ x, const float* __restrict__ p0,
+    const float* __restrict__ p1, const int32_t* __restrict__ level_utt,
+    const int32_t* __restrict__ row_utt, int M, int d, float eps, float k, float c) {
+  constexpr int MAXV = 8;  // d <= 2048
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nv = d / 256 + ((d % 256) ? 1 : 0);
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
+    const float* xr = x + static_cast<size_t>(r) * d;
+    float v[MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int col = i * 256 + lane * 8;
+      if (i < nv && col < d) {
+        const float4 a = *reinterpret_cast<const float4*>(xr + col);
+        const float4 bb = *reinterpret_cast<const float4*>(xr + col + 4);
+        v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+        v[i][4] = bb.x; v[i][5] = bb.y; v[i][6] = bb.z; v[i][7] = bb.w;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += v[i][e];
+      }
+    }
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int col = i * 256 + lane * 8;
+      if (i < nv && col < d) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float dv = v[i][e] - mean; q += dv * dv; }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / d + eps);
+    const float* g;   // gamma (AdaLN: exp(log gamma) row) / LN weight
+    const float* bt;  // beta
+    if (MODE == 0) {
+      const int l = level_utt[row_utt[r]];
+      g = p0 + static_cast<size_t>(l) * 2 * d;
+      bt = g + d;
+    } else {
+      g = p0; bt = p1;
+    }
+    __nv_bfloat16* orow = out + static_cast<size_t>(r) * d;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int col = i * 256 + lane * 8;
+      if (i < nv && col < d) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + col));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + col + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bt + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bt + col + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float y[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float h = (v[i][e] - mean) * rstd;
+          if (MODE == 0) h = c * (1.f - k * h) * h;
+          y[e] = gg[e] * h + bb[e];
+        }
+        uint4 o;
+        o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+        o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+        *reinterpret_cast<uint4*>(orow + col) = o;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_rows_bf16_kernel(
+    __nv_bfloat16* __restrict__ out, const float* __restrict__ x,
+    const int32_t* __restrict__ row_index, int n_rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += gridDim.x * wpb) {
+    const float* xr = x + static_cast<size_t>(row_index[r]) * d;
+    __nv_bfloat16* orow = out + static_cast<size_t>(r) * d;
+    for (int c = lane * 8; c < d; c += 256) {
+      const float4 a = *reinterpret_cast<const float4*>(xr + c);
+      const float4 b = *reinterpret_cast<const float4*>(xr + c + 4);
+      uint4 o;
+      o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+      o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+      *reinterpret_cast<uint4*>(orow + c) = o;
+    }
+  }
+}
+
+static int row_grid(int rows, int wpb) {
+  int grid = (rows + wpb - 1) / wpb;
+  const int cap = num_sms() * 16;
+  return grid > cap ? cap : (grid < 1 ? 1 : grid);
+}
+
+}  // namespace vb200
+
+using namespace vb200;
+
+extern "C" int vb200_embed_gather(float* x_out, const void* text_w, const void* prom_w,
+                                  const void* resp_w, const void* sep, const void* time_w,
+                                  const float* pe, const int32_t* text_ids,
+                                  const int32_t* prom_ids, const int32_t* resp_ids,
+                                  const int32_t* utt, const int32_t* row_utt,
+                                  const int32_t* t_utt, int32_t M, int32_t d, int32_t K,
+                                  int32_t resp_levels_in, vb200_stream_t stream) {
+  VB_REQUIRE(x_out && text_w && prom_w && resp_w && sep && pe && utt && row_utt,
+             "embed_gather: null pointer");
+  VB_REQUIRE(!time_w || t_utt, "embed_gather: time_w given without t_utt");
+  VB_REQUIRE(d > 0 && d % 8 == 0, "embed_gather: d=%d must be a positive multiple of 8", d);
+  VB_REQUIRE(resp_levels_in >= 1 && resp_levels_in <= 8, "embed_gather: resp_levels_in=%d not in 1..8", resp_levels_in);
+  if (M <= 0) return VB200_OK;
+  embed_gather_kernel<<<row_grid(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_out, static_cast<const __nv_bfloat16*>(text_w), static_cast<const __nv_bfloat16*>(prom_w),
+      static_cast<const __nv_bfloat16*>(resp_w), static_cast<const __nv_bfloat16*>(sep),
+      static_cast<const __nv_bfloat16*>(time_w), pe, text_ids, prom_ids, resp_ids, utt, row_utt,
+      t_utt, M, d, K, resp_levels_in);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
+}
+
+extern "C" int vb200_adaln(void* out_bf16, const float* x, const float* table,
+                           const int32_t* level_utt, const int32_t* row_utt, int32_t M, int32_t d,
+                           float eps, float k, float c, vb200_stream_t stream) {
+  VB_REQUIRE(out_bf16 && x && table && level_utt && row_utt, "adaln: null pointer");
+  VB_REQUIRE(d > 0 && d % 8 == 0 && d <= 2048, "adaln: d=%d must be a multiple of 8, <= 2048", d);
+  if (M <= 0) return VB200_OK;
+  norm_kernel<0><<<row_grid(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(out_bf16), x, table, nullptr, level_utt, row_utt, M, d, eps, k, c);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
+}
+
+extern "C" int vb200_layernorm(void* out_bf16, const float* x, const float* weight,
+                               const float* bias, int32_t M, int32_t d, float eps,
+                               vb200_stream_t stream) {
+  VB_REQUIRE(out_bf16 && x && weight && bias, "layernorm: null pointer");
+  VB_REQUIRE(d > 0 && d % 8 == 0 && d <= 2048, "layernorm: d=%d must be a multiple of 8, <= 2048", d);
+  if (M <= 0) return VB200_OK;
+  norm_kernel<1><<<row_grid(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(out_bf16), x, weight, bias, nullptr, nullptr, M, d, eps, 0.f, 0.f);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
+}
+
+extern "C" int vb200_gather_rows_bf16(void* out_bf16, const float* x, const int32_t* row_index,
+                                      int32_t n_rows, int32_t d, vb200_stream_t stream) {
+  VB_REQUIRE(out_bf16 && x && row_index, "gather_rows: null pointer");
+  VB_REQUIRE(d > 0 && d % 8 == 0, "gather_rows: d=%d must be a multiple of 8", d);
+  if (n_rows <= 0) return VB200_OK;
+  gather_rows_bf16_kernel<<<row_grid(n_rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(out_bf16), x, row_index, n_rows, d);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
+}

@@ -1,0 +1,252 @@
+"""Denoiser engine: packs a reference-layout state dict for the sm_100a kernels and runs the
+denoiser forward (``base.py:403-443``) and the D3PM reverse loop (``ar_discrete.py:696-780``)
+as a fixed sequence of libvalle_b200 launches on torch's current CUDA stream.
+
+HBM layout
+  * weights: bf16, nn.Linear layout (N, K) == K-major operands for tcgen05; biases / AdaLN tables
+    fp32 (AdaLN table stores exp(log gamma) | beta so the kernel has no transcendental);
+  * activations: utterances packed back to back, M = sum_b T_b rows, no padding rows, so the
+    reference's mask multiplies (base.py:131,193-194,440) have nothing left to zero;
+  * residual stream fp32 (M, d); GEMM inputs bf16; logits fp16 (M_resp, n_out).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+
+def sinusoidal_table(n: int, d_model: int) -> torch.Tensor:
+    """pe[p] = [sin(p w_i) || cos(p w_i)], w_i = exp(-ln(1e4) i / (d/2)) — computed with the same
+    torch ops as the reference (base.py:38-89) so the table is bit-identical to its add_pe."""
+    d_half = d_model // 2
+    omega = torch.exp(-math.log(1e4) * (torch.arange(d_half, dtype=torch.float32) / d_half))
+    ang = omega[None, :] * torch.arange(n)[:, None]
+    return torch.cat([ang.sin(), ang.cos()], dim=-1).contiguous()
+
+
+class PackedWeights:
+    """Device-resident weights in kernel layout, built from a state dict with base.py's keys."""
+
+    def __init__(self, sd: dict, n_heads: int, n_layers: int, norm_type: str, device, max_rows: int = 4096):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise L.VB200Error("PackedWeights needs a CUDA device (no CPU fallback)")
+        bf = lambda t: t.detach().to(dev, torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        self.device = dev
+        self.n_heads, self.n_layers, self.norm_type = n_heads, n_layers, norm_type
+        self.d = int(sd["sep"].shape[0])
+        if self.d % n_heads or self.d // n_heads != 64:
+            raise L.VB200Error(f"head_dim must be 64 (d_model={self.d}, n_heads={n_heads})")
+        self.text_w = bf(sd["text_emb.weight"])
+        self.prom_w = bf(sd["proms_emb.weight"])
+        self.resp_w = bf(sd["resps_emb.weight"])
+        self.K = int(self.prom_w.shape[1])
+        if int(self.resp_w.shape[1]) != self.K:
+            # Kernels index both tables with one class count; AR-style stop tokens are out of scope.
+            raise L.VB200Error("resps_emb and proms_emb must have the same number of classes")
+        self.sep = bf(sd["sep"])
+        self.time_w = bf(sd["time_emb.weight"]) if "time_emb.weight" in sd else None
+        self.layers = []
+        for i in range(n_layers):
+            p = f"blocks.{i}"
+            ly = dict(
+                w_qkv=bf(sd[f"{p}.attn.block.to_qkv.weight"]),
+                w_out=bf(sd[f"{p}.attn.block.to_out.weight"]),
+                b_out=f32(sd[f"{p}.attn.block.to_out.bias"]),
+                w_ff1=bf(sd[f"{p}.ffn.block.0.weight"]), b_ff1=f32(sd[f"{p}.ffn.block.0.bias"]),
+                w_ff2=bf(sd[f"{p}.ffn.block.3.weight"]), b_ff2=f32(sd[f"{p}.ffn.block.3.bias"]),
+            )
+            for which in ("attn", "ffn"):
+                if norm_type == "adaln":
+                    emb = sd[f"{p}.{which}.norm.emb.weight"].detach().float()
+                    logg, beta = emb.chunk(2, dim=-1)
+                    ly[f"norm_{which}"] = f32(torch.cat([logg.exp(), beta], dim=-1))
+                else:
+                    ly[f"norm_{which}"] = (f32(sd[f"{p}.{which}.norm.weight"]), f32(sd[f"{p}.{which}.norm.bias"]))
+            self.layers.append(ly)
+        self.w_cls = bf(sd["classifier.weight"])
+        self.b_cls = f32(sd["classifier.bias"])
+        self.n_out = int(self.w_cls.shape[0])
+        self._pe = None
+        self.ensure_pe(max_rows)
+
+    def ensure_pe(self, n: int) -> torch.Tensor:
+        if self._pe is None or self._pe.shape[0] < n:
+            self._pe = sinusoidal_table(max(n, 1), self.d).to(self.device)
+        return self._pe
+
+
+class BatchLayout:
+    """Packed-row layout of one batch of utterances (host-built once, constant across steps)."""
+
+    def __init__(self, text_list, proms_list, resp_lens, device, gids=None):
+        dev = torch.device(device)
+        B = len(text_list)
+        if B == 0:
+            raise ValueError("empty batch")
+        if not (len(proms_list) == B and len(resp_lens) == B):
+            raise ValueError("text_list, proms_list and resps must have the same length")
+        t_txt = [int(t.shape[0]) for t in text_list]
+        t_prom = [int(p.shape[0]) for p in proms_list]
+        t_resp = [int(r) for r in resp_lens]
+        for p in proms_list:
+            if p.dim() != 2 or p.shape[1] != 8:
+                raise ValueError(f"prompts must be (t, 8) code grids, got {tuple(p.shape)}")
+        rows = [a + 1 + b + 1 + c for a, b, c in zip(t_txt, t_prom, t_resp)]
+        cu = np.zeros(B + 1, dtype=np.int64)
+        cu[1:] = np.cumsum(rows)
+        if cu[-1] >= 2 ** 31:
+            raise ValueError("batch too large for int32 row indices")
+        self.B, self.M, self.max_T = B, int(cu[-1]), int(max(rows))
+        self.t_txt, self.t_prom, self.t_resp, self.rows = t_txt, t_prom, t_resp, rows
+        self.M_resp = int(sum(t_resp))
+        utt = np.zeros((B, L.U_STRIDE), dtype=np.int32)
+        utt[:, L.U_ROW0] = cu[:-1]
+        utt[:, L.U_TTXT], utt[:, L.U_TPROM], utt[:, L.U_TRESP] = t_txt, t_prom, t_resp
+        utt[:, L.U_TXT0] = np.concatenate([[0], np.cumsum(t_txt)[:-1]])
+        utt[:, L.U_PROM0] = np.concatenate([[0], np.cumsum(t_prom)[:-1]])
+        resp0 = np.concatenate([[0], np.cumsum(t_resp)[:-1]])
+        utt[:, L.U_RESP0] = resp0
+        utt[:, L.U_GID] = np.arange(B) if gids is None else np.asarray(gids)
+        row_utt = np.repeat(np.arange(B, dtype=np.int32), rows)
+        resp_row_utt = np.repeat(np.arange(B, dtype=np.int32), t_resp)
+        resp_row_index = np.concatenate(
+            [np.arange(cu[b + 1] - t_resp[b], cu[b + 1], dtype=np.int32) for b in range(B)]
+        ) if self.M_resp else np.zeros(0, dtype=np.int32)
+        self.resp_offsets = resp0.tolist()
+
+        def up(a):
+            return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().to(dev, non_blocking=True)
+
+        self.utt, self.row_utt, self.cu_rows = up(utt), up(row_utt), up(cu.astype(np.int32))
+        self.resp_row_utt, self.resp_row_index = up(resp_row_utt), up(resp_row_index)
+        text = torch.cat([t.reshape(-1) for t in text_list]).to(torch.int32)
+        proms = torch.cat([p.reshape(-1, 8) for p in proms_list]).to(torch.int32)
+        self.text_ids = text.contiguous().to(dev, non_blocking=True)
+        self.prom_ids = proms.contiguous().to(dev, non_blocking=True)
+        self.h2d_bytes = int(utt.nbytes + row_utt.nbytes + (B + 1) * 4 + resp_row_utt.nbytes +
+                             resp_row_index.nbytes + text.numel() * 4 + proms.numel() * 4)
+        self.device = dev
+
+    def split_resp(self, packed: torch.Tensor):
+        """(M_resp, ...) packed response rows -> list of per-utterance tensors."""
+        return list(packed.split(self.t_resp, dim=0))
+
+
+@dataclass
+class Workspace:
+    x: torch.Tensor
+    h: torch.Tensor
+    qkv: torch.Tensor
+    att: torch.Tensor
+    ff: torch.Tensor
+    head_in: torch.Tensor
+    logits: torch.Tensor
+    extra: dict = field(default_factory=dict)
+
+
+class DenoiserEngine:
+    """Runs the packed denoiser forward and the reverse loop for one PackedWeights."""
+
+    def __init__(self, weights: PackedWeights, logits_dtype=torch.float16, attn_variant="tmem", simt=False):
+        self.w = weights
+        self.logits_dtype = logits_dtype
+        self.attn_variant = attn_variant
+        self.simt = simt      # validation only: route GEMM/attention through the CUDA-core kernels
+        self.launches = 0     # kernels launched by this engine (bench.py reports it)
+
+    # ------------------------------------------------------------------ buffers
+    def workspace(self, lay: BatchLayout, logits_dtype=None) -> Workspace:
+        w, dev = self.w, self.w.device
+        d, M, Mr = w.d, lay.M, lay.M_resp
+        e = lambda *s, dt: torch.empty(*s, dtype=dt, device=dev)
+        w.ensure_pe(lay.max_T)
+        return Workspace(
+            x=e(M, d, dt=torch.float32), h=e(M, d, dt=torch.bfloat16), qkv=e(M, 3 * d, dt=torch.bfloat16),
+            att=e(M, d, dt=torch.bfloat16), ff=e(M, 4 * d, dt=torch.bfloat16),
+            head_in=e(Mr, d, dt=torch.bfloat16), logits=e(Mr, w.n_out, dt=logits_dtype or self.logits_dtype))
+
+    # ------------------------------------------------------------------ one denoiser forward
+    def forward(self, lay: BatchLayout, ws: Workspace, resp_ids: torch.Tensor, level_utt: torch.Tensor,
+                use_time: bool, hidden_out: list | None = None) -> torch.Tensor:
+        """resp_ids int32 (M_resp, levels_in); level_utt int32 (B) = AdaLN row (and time_emb row when
+        use_time).  Returns ws.logits (M_resp, n_out): classifier(x) on the response rows."""
+        w = self.w
+        sv = self.simt
+        levels_in = int(resp_ids.shape[1])
+        L.embed_gather(ws.x, w.text_w, w.prom_w, w.resp_w, w.sep, w.time_w if use_time else None,
+                       w.ensure_pe(lay.max_T), lay.text_ids, lay.prom_ids, resp_ids, lay.utt, lay.row_utt,
+                       level_utt, w.K, levels_in)
+        scale = 64 ** -0.5
+        for ly in w.layers:
+            self._norm(ws.h, ws.x, ly["norm_attn"], level_utt, lay)
+            L.gemm_bf16(ws.qkv, ws.h, ly["w_qkv"], epi=L.EPI_NONE, simt=sv)
+            L.flash_attn_varlen(ws.att, ws.qkv, lay.cu_rows, lay.max_T, w.n_heads, scale,
+                                variant="simt" if sv else self.attn_variant)
+            L.gemm_bf16(ws.x, ws.att, ly["w_out"], ly["b_out"], residual=ws.x, epi=L.EPI_BIAS_RESIDUAL, simt=sv)
+            self._norm(ws.h, ws.x, ly["norm_ffn"], level_utt, lay)
+            L.gemm_bf16(ws.ff, ws.h, ly["w_ff1"], ly["b_ff1"], epi=L.EPI_BIAS_GELU, simt=sv)
+            L.gemm_bf16(ws.x, ws.ff, ly["w_ff2"], ly["b_ff2"], residual=ws.x, epi=L.EPI_BIAS_RESIDUAL, simt=sv)
+            if hidden_out is not None:
+                hidden_out.append(ws.x.clone())
+        L.gather_rows_bf16(ws.head_in, ws.x, lay.resp_row_index)
+        L.gemm_bf16(ws.logits, ws.head_in, w.w_cls, w.b_cls, epi=L.EPI_BIAS, simt=sv)
+        self.launches += 1 + 7 * len(w.layers) + 2
+        return ws.logits
+
+    def _norm(self, out, x, params, level_utt, lay):
+        if self.w.norm_type == "adaln":
+            L.adaln(out, x, params, level_utt, lay.row_utt)
+        else:
+            L.layernorm(out, x, params[0], params[1])
+
+    # ------------------------------------------------------------------ reverse loop
+    def reverse_loop(self, lay: BatchLayout, ws: Workspace, x_t: torch.Tensor, table: torch.Tensor,
+                     timesteps: int, transition: int, noise: int = L.NOISE_PHILOX, seed: int = 0,
+                     uniforms_fn=None, use_graph: bool = True, n_levels: int = 8, trace: list | None = None):
+        """x_T -> x_0 in place on x_t int32 (M_resp, n_levels): for t = S-1 .. 1 (never t = 0, as the
+        reference, ar_discrete.py:750): logits = denoiser(x_t, t); x_{t-1} = p_sample(logits, t, x_t).
+        uniforms_fn(t) -> float32 (M_resp*n_levels, K) supplies the reference's torch.rand in parity mode."""
+        w, dev = self.w, self.w.device
+        K = w.n_out // n_levels
+        t_utt = torch.full((lay.B,), timesteps - 1, dtype=torch.int32, device=dev)
+
+        def one_step(uniforms=None):
+            logits = self.forward(lay, ws, x_t, t_utt, use_time=True)
+            L.posterior_sample_from_logits(x_t, None, logits, w.n_out, x_t, lay.resp_row_utt, t_utt, lay.utt,
+                                           table, lay.M_resp, n_levels, K, transition, noise, uniforms, seed)
+            L.step_timesteps(t_utt, -1)
+            self.launches += 2
+
+        n_steps = timesteps - 1
+        graph_ok = use_graph and noise != L.NOISE_UNIFORMS and trace is None and n_steps > 2
+        if not graph_ok:
+            for t in range(timesteps - 1, 0, -1):
+                one_step(uniforms_fn(t) if noise == L.NOISE_UNIFORMS else None)
+                if trace is not None:
+                    trace.append(x_t.clone())
+            return x_t
+        # First step eagerly (also warms tensor-map caches and function attributes), then capture
+        # one step and replay it: the timestep lives in device memory, so the graph is step-invariant.
+        one_step()
+        g = torch.cuda.CUDAGraph()
+        cap_stream = torch.cuda.Stream(device=dev)
+        cap_stream.wait_stream(torch.cuda.current_stream(dev))
+        launches_before = self.launches
+        with torch.cuda.stream(cap_stream):
+            with torch.cuda.graph(g, stream=cap_stream):
+                one_step()
+        per_step = self.launches - launches_before
+        self.launches = launches_before
+        torch.cuda.current_stream(dev).wait_stream(cap_stream)
+        for _ in range(n_steps - 1):
+            g.replay()
+            self.launches += per_step
+        ws.extra["graph"] = g
+        return x_t

@@ -1,0 +1,164 @@
+"""ctypes binding of libvalle_b200.so (C ABI declared in include/vb200.h).
+
+There is no fallback: if the library is missing or a call fails, this raises.  Tensors are
+passed as raw device pointers; every call runs on torch's current CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libvalle_b200.so"
+
+OK = 0
+F32, BF16, F16 = 0, 1, 2
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2, 3
+ABSORBING, UNIFORM = 0, 1
+NOISE_PHILOX, NOISE_UNIFORMS, NOISE_GREEDY = 0, 1, 2
+U_ROW0, U_TTXT, U_TPROM, U_TRESP, U_TXT0, U_PROM0, U_RESP0, U_GID, U_STRIDE = range(9)
+(TAB_ONE_KEEP, TAB_ONE_OFF, TAB_ONE_ABSORB, TAB_ONE_BOTH, TAB_CUM_KEEP, TAB_CUM_OFF, TAB_CUM_ABSORB,
+ TAB_CUM_BOTH, TAB_LOG_KEEP, TAB_LOG_OFF, TAB_LOG_ABSORB, TAB_LOG_BOTH, TAB_STRIDE) = range(13)
+
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+_p, _i32, _i64, _u64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+
+# name -> argtypes; must list every symbol include/vb200.h declares (tests check this)
+PROTOTYPES = {
+    "vb200_last_error": ([], C.c_char_p),
+    "vb200_version": ([], C.c_int),
+    "vb200_device_sms": ([], C.c_int),
+    "vb200_embed_gather": ([_p] * 13 + [_i32] * 4 + [_p], C.c_int),
+    "vb200_adaln": ([_p] * 5 + [_i32, _i32, _f, _f, _f, _p], C.c_int),
+    "vb200_layernorm": ([_p] * 4 + [_i32, _i32, _f, _p], C.c_int),
+    "vb200_gather_rows_bf16": ([_p] * 3 + [_i32, _i32, _p], C.c_int),
+    "vb200_gemm_bf16": ([_p, C.c_int, _p, _p, _p, _p, _i32, _i32, _i32, C.c_int, _p], C.c_int),
+    "vb200_gemm_bf16_simt": ([_p, C.c_int, _p, _p, _p, _p, _i32, _i32, _i32, C.c_int, _p], C.c_int),
+    "vb200_flash_attn_varlen": ([_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p], C.c_int),
+    "vb200_flash_attn_varlen_psmem": ([_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p], C.c_int),
+    "vb200_attn_varlen_simt": ([_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p], C.c_int),
+    "vb200_q_sample": ([_p] * 6 + [_i32, _i32, _i32, C.c_int, _p], C.c_int),
+    "vb200_posterior_sample_from_logits": (
+        [_p, _p, _p, C.c_int, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, C.c_int, C.c_int, _p, _u64, _p],
+        C.c_int),
+    "vb200_step_timesteps": ([_p, _i32, _i32, _p], C.c_int),
+}
+
+_lib = None
+
+
+class VB200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Loads the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise VB200Error(
+            f"{LIB_PATH} is missing: build it with `python tts-with-diffusion-model_b200/build.py` "
+            "(the CUDA library is the only implementation of the hot path; there is no fallback)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (argtypes, restype) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().vb200_last_error().decode("utf-8", "replace")
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != OK:
+        raise VB200Error(f"{what} failed with status {rc}: {last_error()}")
+
+
+def ptr(t: torch.Tensor | None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise VB200Error("vb200 kernels take CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise VB200Error("vb200 kernels take contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    return _DTYPES[dt]
+
+
+# ------------------------------------------------------------------ thin typed wrappers
+def embed_gather(x_out, text_w, prom_w, resp_w, sep, time_w, pe, text_ids, prom_ids, resp_ids, utt,
+                 row_utt, t_utt, K, resp_levels_in):
+    M, d = x_out.shape
+    _check(load().vb200_embed_gather(ptr(x_out), ptr(text_w), ptr(prom_w), ptr(resp_w), ptr(sep),
+                                     ptr(time_w), ptr(pe), ptr(text_ids), ptr(prom_ids), ptr(resp_ids),
+                                     ptr(utt), ptr(row_utt), ptr(t_utt), M, d, K, resp_levels_in,
+                                     stream()), "vb200_embed_gather")
+
+
+def adaln(out, x, table, level_utt, row_utt, eps=1e-5, k=0.1, c=2.0):
+    M, d = x.shape
+    _check(load().vb200_adaln(ptr(out), ptr(x), ptr(table), ptr(level_utt), ptr(row_utt), M, d, eps, k, c,
+                              stream()), "vb200_adaln")
+
+
+def layernorm(out, x, weight, bias, eps=1e-5):
+    M, d = x.shape
+    _check(load().vb200_layernorm(ptr(out), ptr(x), ptr(weight), ptr(bias), M, d, eps, stream()),
+           "vb200_layernorm")
+
+
+def gather_rows_bf16(out, x, row_index):
+    n, d = out.shape
+    _check(load().vb200_gather_rows_bf16(ptr(out), ptr(x), ptr(row_index), n, d, stream()),
+           "vb200_gather_rows_bf16")
+
+
+def gemm_bf16(out, A, W, bias=None, residual=None, epi=EPI_NONE, simt=False):
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == K and tuple(out.shape) == (M, N), (A.shape, W.shape, out.shape)
+    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+    fn = load().vb200_gemm_bf16_simt if simt else load().vb200_gemm_bf16
+    _check(fn(ptr(out), dtype_code(out.dtype), ptr(A), ptr(W), ptr(bias), ptr(residual), M, N, K, epi,
+              stream()), "vb200_gemm_bf16")
+
+
+def flash_attn_varlen(out, qkv, cu_rows, max_T, n_heads, scale, variant="tmem"):
+    M = qkv.shape[0]
+    B = cu_rows.numel() - 1
+    fn = {"tmem": load().vb200_flash_attn_varlen, "psmem": load().vb200_flash_attn_varlen_psmem,
+          "simt": load().vb200_attn_varlen_simt}[variant]
+    _check(fn(ptr(out), ptr(qkv), ptr(cu_rows), B, max_T, M, n_heads, scale, stream()),
+           f"vb200_flash_attn_varlen[{variant}]")
+
+
+def q_sample(x_out, x0, t_tok, mask, uniforms, table, K, transition):
+    n = x0.numel()
+    _check(load().vb200_q_sample(ptr(x_out), ptr(x0), ptr(t_tok), ptr(mask), ptr(uniforms), ptr(table), n, K,
+                                 table.shape[0], transition, stream()), "vb200_q_sample")
+
+
+def posterior_sample_from_logits(x_out, post_out, logits, ld_logits, x_t, row_utt, t_utt, utt, table,
+                                 n_rows, n_levels, K, transition, noise, uniforms=None, seed=0):
+    _check(load().vb200_posterior_sample_from_logits(
+        ptr(x_out), ptr(post_out), ptr(logits), dtype_code(logits.dtype), ld_logits, ptr(x_t),
+        ptr(row_utt), ptr(t_utt), ptr(utt), ptr(table), n_rows, n_levels, K, table.shape[0], transition,
+        noise, ptr(uniforms), seed, stream()), "vb200_posterior_sample_from_logits")
+
+
+def step_timesteps(t_utt, delta):
+    _check(load().vb200_step_timesteps(ptr(t_utt), t_utt.numel(), delta, stream()), "vb200_step_timesteps")

@@ -1,0 +1,72 @@
+"""Host-side D3PM constants for the CUDA reverse step.
+
+The reference keeps three dense (S, K, K) fp16 tensors (``ar_discrete.py:257-277``: one-step
+matrices, their fp16 chain product ``q_mats`` and the transposes, 3 x 210 MB at S=100, K=1025) and
+indexes them with one-hot matmuls.  Both transition families have rank-structured matrices, so the
+kernels only need a few scalars per timestep.  To keep those scalars *bit-identical* to what the
+reference holds (the fp16 chain product drifts from the analytic value — row sums reach 1.002 —
+and ``eps=1e-6`` makes that drift observable), they are read out of the same fp16 chain product,
+computed here once with a running (K, K) matrix instead of being re-derived from alpha-bar.
+"""
+from __future__ import annotations
+
+import functools
+
+import numpy as np
+import torch
+
+from ..b200 import lib as L
+
+EPS = 1.0e-6  # ar_discrete.py:276
+
+
+def cosine_beta_schedule(timesteps: int, s: float = 0.008) -> torch.Tensor:
+    """Cosine schedule with the reference's grid: ``steps`` points spread over [0, steps]
+    (not [0, 1]) before normalising by ``steps`` (ar_discrete.py:286-304)."""
+    steps = timesteps + 1
+    grid = np.linspace(0, steps, steps)
+    abar = np.cos(((grid / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    abar = abar / abar[0]
+    betas = np.clip(1 - (abar[1:] / abar[:-1]), a_min=0, a_max=0.999)
+    return torch.from_numpy(betas)
+
+
+def _onestep(beta_t: torch.Tensor, K: int, transition: str) -> torch.Tensor:
+    if transition == "absorbing":      # (1-b) I + b 1 e_m^T, float64 then fp16 (ar_discrete.py:315-334,269)
+        b = float(beta_t.numpy())
+        q = torch.zeros(K, K, dtype=torch.float64)
+        q.fill_diagonal_(1.0 - b)
+        q[:, K // 2] += b
+        return q.to(torch.float16)
+    if transition == "uniform":        # fp16 from the start (ar_discrete.py:308-313)
+        q = torch.full((K, K), beta_t / K).to(torch.float16)
+        q.fill_diagonal_(1.0 - beta_t * (K - 1) / K)
+        return q
+    raise ValueError(f"unknown transition {transition!r} (expected 'absorbing' or 'uniform')")
+
+
+@functools.lru_cache(maxsize=16)
+def scalar_table(timesteps: int, K: int, transition: str) -> torch.Tensor:
+    """float32 (S, TAB_STRIDE) table for vb200_q_sample / vb200_posterior_sample_from_logits."""
+    betas = cosine_beta_schedule(timesteps + 1).to(torch.float16)     # ar_discrete.py:257
+    m = K // 2
+    a = 0 if m != 0 else 1
+    b = 1 if m != 1 else 2
+    tab = torch.zeros(timesteps, L.TAB_STRIDE, dtype=torch.float32)
+    cum = None
+    for t in range(timesteps):
+        one = _onestep(betas[t], K, transition)
+        cum = one if cum is None else torch.tensordot(cum, one, dims=[[1], [0]])  # fp16, :270-274
+        tab[t, L.TAB_ONE_KEEP] = one[a, a]
+        tab[t, L.TAB_ONE_OFF] = one[a, b]
+        tab[t, L.TAB_ONE_ABSORB] = one[a, m]
+        tab[t, L.TAB_ONE_BOTH] = one[m, m]
+        picks = torch.stack([cum[a, a], cum[a, b], cum[a, m], cum[m, m]])
+        tab[t, L.TAB_CUM_KEEP:L.TAB_CUM_BOTH + 1] = picks.float()
+        # q_sample logits are formed in fp16: log(fp16(q) + eps) (ar_discrete.py:482)
+        tab[t, L.TAB_LOG_KEEP:L.TAB_LOG_BOTH + 1] = torch.log(picks + EPS).float()
+    return tab
+
+
+def betas_fp16(timesteps: int) -> torch.Tensor:
+    return cosine_beta_schedule(timesteps + 1).to(torch.float16)
