@@ -9,14 +9,15 @@ cmd = [sys.executable, "-m", "pytest", "tests", "-m", "gpu", "--collect-only", "
 if sel:
     cmd += ["-k", sel]
 ids = [l.strip() for l in subprocess.run(cmd, capture_output=True, text=True).stdout.splitlines() if "::" in l]
+ids = list(dict.fromkeys(i.split("[")[0] for i in ids))      # one process per test function
 print(f"{len(ids)} tests", flush=True)
 fails = 0
 for tid in ids:
     try:
-        r = subprocess.run([sys.executable, "-m", "pytest", tid, "-x", "-q", "--no-header", "-p", "no:cacheprovider"],
-                           capture_output=True, text=True, timeout=240)
+        r = subprocess.run([sys.executable, "-m", "pytest", tid, "-q", "--no-header", "-p", "no:cacheprovider", "--tb=short"],
+                           capture_output=True, text=True, timeout=400)
         ok = r.returncode == 0
-        tail = "" if ok else "\n".join((r.stdout + r.stderr).splitlines()[-25:])
+        tail = "" if ok else "\n".join((r.stdout + r.stderr).splitlines()[-60:])
     except subprocess.TimeoutExpired:
         ok, tail = False, "TIMEOUT"
     fails += not ok
