@@ -110,12 +110,12 @@ def test_adaln_layernorm_gather(L):
     table = torch.cat([emb[:, :d].exp(), emb[:, d:]], dim=-1).to(DEV)
     out = torch.empty(M, d, dtype=torch.bfloat16, device=DEV)
     L.adaln(out, x.to(DEV), table, lv.to(DEV), row_utt.to(DEV))
-    assert (out.float().cpu() - ref).abs().max().item() < 3e-2
-    assert (out.float().cpu() - ref.bfloat16().float()).abs().max().item() < 3e-2
+    # output is bf16: allow one bf16 ulp (2^-7 relative) on top of fp32 round-off
+    assert ((out.float().cpu() - ref).abs() <= ref.abs() * 2 ** -7 + 1e-3).all()
     w, b = torch.randn(d, generator=g), torch.randn(d, generator=g)
     ref = torch.nn.functional.layer_norm(x, (d,), w, b, 1e-5)
     L.layernorm(out, x.to(DEV), w.to(DEV), b.to(DEV))
-    assert (out.float().cpu() - ref).abs().max().item() < 5e-2
+    assert ((out.float().cpu() - ref).abs() <= ref.abs() * 2 ** -7 + 1e-3).all()
     idx = torch.tensor([5, 0, 332, 17], dtype=torch.int32)
     o2 = torch.empty(4, d, dtype=torch.bfloat16, device=DEV)
     L.gather_rows_bf16(o2, x.to(DEV), idx.to(DEV))

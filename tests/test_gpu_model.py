@@ -102,7 +102,7 @@ def test_hidden_states_vs_oracle_and_simt_path():
     simt = DenoiserEngine(eng.w, simt=True)
     ws2 = simt.workspace(lay, logits_dtype=torch.float32)
     logits2 = simt.forward(lay, ws2, resp, t.to(DEV, torch.int32), use_time=True)
-    assert (logits - logits2).abs().max().item() < 1e-2
+    assert (logits - logits2).abs().max().item() < 3e-2     # two bf16 pipelines, different summation orders
 
 
 @pytest.mark.parametrize("transition", ["absorbing", "uniform"])

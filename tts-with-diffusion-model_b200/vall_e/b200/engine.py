@@ -160,6 +160,7 @@ class DenoiserEngine:
         self.attn_variant = attn_variant
         self.simt = simt      # validation only: route GEMM/attention through the CUDA-core kernels
         self.launches = 0     # kernels launched by this engine (bench.py reports it)
+        self.profile = None   # bench.py: list collecting (kind, flops, start_event, end_event) per GEMM/attention launch
 
     # ------------------------------------------------------------------ buffers
     def workspace(self, lay: BatchLayout, logits_dtype=None) -> Workspace:
@@ -184,21 +185,43 @@ class DenoiserEngine:
                        w.ensure_pe(lay.max_T), lay.text_ids, lay.prom_ids, resp_ids, lay.utt, lay.row_utt,
                        level_utt, w.K, levels_in)
         scale = 64 ** -0.5
+        gemm, attn_flops = self._gemm, sum(4 * T * T * w.d for T in lay.rows)
         for ly in w.layers:
             self._norm(ws.h, ws.x, ly["norm_attn"], level_utt, lay)
-            L.gemm_bf16(ws.qkv, ws.h, ly["w_qkv"], epi=L.EPI_NONE, simt=sv)
+            gemm(ws.qkv, ws.h, ly["w_qkv"], epi=L.EPI_NONE)
+            ev = self._prof_begin()
             L.flash_attn_varlen(ws.att, ws.qkv, lay.cu_rows, lay.max_T, w.n_heads, scale,
                                 variant="simt" if sv else self.attn_variant)
-            L.gemm_bf16(ws.x, ws.att, ly["w_out"], ly["b_out"], residual=ws.x, epi=L.EPI_BIAS_RESIDUAL, simt=sv)
+            self._prof_end(ev, "attn", attn_flops)
+            gemm(ws.x, ws.att, ly["w_out"], ly["b_out"], residual=ws.x, epi=L.EPI_BIAS_RESIDUAL)
             self._norm(ws.h, ws.x, ly["norm_ffn"], level_utt, lay)
-            L.gemm_bf16(ws.ff, ws.h, ly["w_ff1"], ly["b_ff1"], epi=L.EPI_BIAS_GELU, simt=sv)
-            L.gemm_bf16(ws.x, ws.ff, ly["w_ff2"], ly["b_ff2"], residual=ws.x, epi=L.EPI_BIAS_RESIDUAL, simt=sv)
+            gemm(ws.ff, ws.h, ly["w_ff1"], ly["b_ff1"], epi=L.EPI_BIAS_GELU)
+            gemm(ws.x, ws.ff, ly["w_ff2"], ly["b_ff2"], residual=ws.x, epi=L.EPI_BIAS_RESIDUAL)
             if hidden_out is not None:
                 hidden_out.append(ws.x.clone())
         L.gather_rows_bf16(ws.head_in, ws.x, lay.resp_row_index)
-        L.gemm_bf16(ws.logits, ws.head_in, w.w_cls, w.b_cls, epi=L.EPI_BIAS, simt=sv)
+        gemm(ws.logits, ws.head_in, w.w_cls, w.b_cls, epi=L.EPI_BIAS)
         self.launches += 1 + 7 * len(w.layers) + 2
         return ws.logits
+
+    def _gemm(self, out, A, W, bias=None, residual=None, epi=L.EPI_NONE):
+        ev = self._prof_begin()
+        L.gemm_bf16(out, A, W, bias, residual=residual, epi=epi, simt=self.simt)
+        self._prof_end(ev, "gemm", 2 * A.shape[0] * A.shape[1] * W.shape[0])
+
+    def _prof_begin(self):
+        if self.profile is None:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    def _prof_end(self, ev, kind, flops):
+        if ev is None:
+            return
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        self.profile.append((kind, flops, ev, end))
 
     def _norm(self, out, x, params, level_utt, lay):
         if self.w.norm_type == "adaln":
@@ -207,46 +230,102 @@ class DenoiserEngine:
             L.layernorm(out, x, params[0], params[1])
 
     # ------------------------------------------------------------------ reverse loop
+    def session(self, lay: BatchLayout) -> "Session":
+        return Session(self, lay)
+
     def reverse_loop(self, lay: BatchLayout, ws: Workspace, x_t: torch.Tensor, table: torch.Tensor,
                      timesteps: int, transition: int, noise: int = L.NOISE_PHILOX, seed: int = 0,
                      uniforms_fn=None, use_graph: bool = True, n_levels: int = 8, trace: list | None = None):
-        """x_T -> x_0 in place on x_t int32 (M_resp, n_levels): for t = S-1 .. 1 (never t = 0, as the
-        reference, ar_discrete.py:750): logits = denoiser(x_t, t); x_{t-1} = p_sample(logits, t, x_t).
-        uniforms_fn(t) -> float32 (M_resp*n_levels, K) supplies the reference's torch.rand in parity mode."""
-        w, dev = self.w, self.w.device
+        """One-shot form (tests): x_T -> x_0 in place on x_t int32 (M_resp, n_levels)."""
+        ses = Session(self, lay, ws=ws, x_t=x_t)
+        ses.run(table, timesteps, transition, noise=noise, seed=seed, uniforms_fn=uniforms_fn,
+                use_graph=use_graph, n_levels=n_levels, trace=trace)
+        return x_t
+
+
+class Session:
+    """Persistent device state for batches of one shape signature: layout arrays, workspace, x_t,
+    the per-utterance timestep vector and (after the first run) a CUDA graph of one denoise step.
+    A new batch with the same per-utterance lengths is ``load``-ed into the same buffers, so the
+    captured graph is replayed unchanged."""
+
+    def __init__(self, engine: DenoiserEngine, lay: BatchLayout, ws: Workspace | None = None,
+                 x_t: torch.Tensor | None = None, n_levels: int = 8):
+        self.eng, self.lay = engine, lay
+        dev = engine.w.device
+        self.ws = ws if ws is not None else engine.workspace(lay)
+        self.x_t = x_t if x_t is not None else torch.empty(lay.M_resp, n_levels, dtype=torch.int32, device=dev)
+        self.t_utt = torch.zeros(lay.B, dtype=torch.int32, device=dev)
+        self.graph = None
+        self.graph_key = None
+        self.per_step_launches = 0
+
+    def signature(self):
+        return (tuple(self.lay.t_txt), tuple(self.lay.t_prom), tuple(self.lay.t_resp))
+
+    def load(self, text_list, proms_list, gids=None) -> int:
+        """Copies a new same-shape batch (host or device tensors) into the session's buffers.
+        Returns the bytes moved host->device."""
+        lay = self.lay
+        if [len(t) for t in text_list] != lay.t_txt or [len(p) for p in proms_list] != lay.t_prom:
+            raise ValueError("batch shape does not match this session")
+        text = torch.cat([t.reshape(-1) for t in text_list]).to(torch.int32)
+        proms = torch.cat([p.reshape(-1, 8) for p in proms_list]).to(torch.int32)
+        lay.text_ids.copy_(text, non_blocking=True)
+        lay.prom_ids.copy_(proms, non_blocking=True)
+        moved = (text.numel() + proms.numel()) * 4
+        if gids is not None:
+            g = torch.as_tensor(gids, dtype=torch.int32)
+            lay.utt[:, L.U_GID].copy_(g, non_blocking=True)
+            moved += g.numel() * 4
+        return moved
+
+    def run(self, table: torch.Tensor, timesteps: int, transition: int, noise: int = L.NOISE_PHILOX,
+            seed: int = 0, uniforms_fn=None, use_graph: bool = True, n_levels: int = 8,
+            trace: list | None = None) -> torch.Tensor:
+        """for t = S-1 .. 1 (never t = 0, as the reference, ar_discrete.py:750):
+        logits = denoiser(x_t, t); x_{t-1} = p_sample(logits, t, x_t), in place on self.x_t.
+        uniforms_fn(t) -> float32 (M_resp*n_levels, K) supplies the reference's torch.rand (parity)."""
+        eng, lay, ws, x_t, t_utt = self.eng, self.lay, self.ws, self.x_t, self.t_utt
+        w, dev = eng.w, eng.w.device
         K = w.n_out // n_levels
-        t_utt = torch.full((lay.B,), timesteps - 1, dtype=torch.int32, device=dev)
+        t_utt.fill_(timesteps - 1)
 
         def one_step(uniforms=None):
-            logits = self.forward(lay, ws, x_t, t_utt, use_time=True)
+            logits = eng.forward(lay, ws, x_t, t_utt, use_time=True)
             L.posterior_sample_from_logits(x_t, None, logits, w.n_out, x_t, lay.resp_row_utt, t_utt, lay.utt,
                                            table, lay.M_resp, n_levels, K, transition, noise, uniforms, seed)
             L.step_timesteps(t_utt, -1)
-            self.launches += 2
+            eng.launches += 2
 
         n_steps = timesteps - 1
-        graph_ok = use_graph and noise != L.NOISE_UNIFORMS and trace is None and n_steps > 2
+        graph_ok = (use_graph and noise != L.NOISE_UNIFORMS and trace is None and n_steps > 2
+                    and eng.profile is None)
         if not graph_ok:
             for t in range(timesteps - 1, 0, -1):
                 one_step(uniforms_fn(t) if noise == L.NOISE_UNIFORMS else None)
                 if trace is not None:
                     trace.append(x_t.clone())
             return x_t
-        # First step eagerly (also warms tensor-map caches and function attributes), then capture
-        # one step and replay it: the timestep lives in device memory, so the graph is step-invariant.
-        one_step()
-        g = torch.cuda.CUDAGraph()
-        cap_stream = torch.cuda.Stream(device=dev)
-        cap_stream.wait_stream(torch.cuda.current_stream(dev))
-        launches_before = self.launches
-        with torch.cuda.stream(cap_stream):
-            with torch.cuda.graph(g, stream=cap_stream):
-                one_step()
-        per_step = self.launches - launches_before
-        self.launches = launches_before
-        torch.cuda.current_stream(dev).wait_stream(cap_stream)
-        for _ in range(n_steps - 1):
-            g.replay()
-            self.launches += per_step
-        ws.extra["graph"] = g
+        key = (table.data_ptr(), transition, noise, seed, n_levels)
+        first = 0
+        if self.graph is None or self.graph_key != key:
+            # First step eagerly (also warms tensor-map caches and function attributes), then capture
+            # one step: the timestep lives in device memory, so the graph is step-invariant.
+            one_step()
+            first = 1
+            g = torch.cuda.CUDAGraph()
+            cap_stream = torch.cuda.Stream(device=dev)
+            cap_stream.wait_stream(torch.cuda.current_stream(dev))
+            before = eng.launches
+            with torch.cuda.stream(cap_stream):
+                with torch.cuda.graph(g, stream=cap_stream):
+                    one_step()
+            self.per_step_launches = eng.launches - before
+            eng.launches = before
+            torch.cuda.current_stream(dev).wait_stream(cap_stream)
+            self.graph, self.graph_key = g, key
+        for _ in range(n_steps - first):
+            self.graph.replay()
+            eng.launches += self.per_step_launches
         return x_t
