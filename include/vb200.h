@@ -122,11 +122,6 @@ int vb200_gemm_bf16_simt(void* out, vb200_dtype out_dtype, const void* A, const 
 int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, const int32_t* cu_rows,
                             int32_t B, int32_t max_T, int32_t M, int32_t n_heads, float scale,
                             vb200_stream_t stream);
-/* Same contract; P = softmax block goes through shared memory instead of TMEM (bring-up variant
- * kept for A/B tests of the two tcgen05 operand paths). */
-int vb200_flash_attn_varlen_psmem(void* out_bf16, const void* qkv_bf16, const int32_t* cu_rows,
-                                  int32_t B, int32_t max_T, int32_t M, int32_t n_heads,
-                                  float scale, vb200_stream_t stream);
 /* Same contract, one-warp-per-query CUDA-core kernel.  Validation aid only. */
 int vb200_attn_varlen_simt(void* out_bf16, const void* qkv_bf16, const int32_t* cu_rows,
                            int32_t B, int32_t max_T, int32_t M, int32_t n_heads, float scale,

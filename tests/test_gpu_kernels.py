@@ -83,8 +83,8 @@ def _attn_ref(qkv, lens, n_heads):
     return torch.cat(outs)
 
 
-@pytest.mark.parametrize("variant", ["tmem", "psmem", "simt"])
-@pytest.mark.parametrize("lens,heads", [([5], 1), ([128], 2), ([129, 64, 300], 2), ([1027], 4), ([257, 1, 640], 3)])
+@pytest.mark.parametrize("variant", ["tmem", "simt"])
+@pytest.mark.parametrize("lens,heads", [([5], 1), ([128], 2), ([129, 64, 300], 2), ([1027], 4), ([257, 1, 640], 3), ([256, 255, 385, 16, 17], 2), ([2527], 2)])
 def test_attention(L, variant, lens, heads):
     M, d = sum(lens), heads * 64
     qkv = _rand_bf16((M, 3 * d), 5)

@@ -56,7 +56,7 @@ if __name__ == "__main__":
         gemm(M, 4096, 1024, L.EPI_BIAS_GELU, torch.bfloat16)
         gemm(M, 1024, 4096, L.EPI_BIAS_RESIDUAL, torch.float32)
     gemm(750 * 32, 8192, 1024, L.EPI_BIAS, torch.float16)
-    for v in ("tmem", "psmem"):
+    for v in ("tmem",):
         try:
             attn([1027] * 32, 16, v)
             attn([2527] * 8, 16, v)

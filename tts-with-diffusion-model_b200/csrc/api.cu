@@ -3,6 +3,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
 
 namespace vb200 {
@@ -53,8 +57,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t outer,
-                      uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+int make_tmap_2d(CUtensorMap* out, vb200_dtype dtype, const void* gptr, uint64_t inner,
+                 uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled driver entry point unavailable");
@@ -69,7 +73,10 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t elem[2] = {1, 1};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides,
+  const CUtensorMapDataType dt = dtype == VB200_F32   ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == VB200_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                                                      : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(gptr), dims, strides,
                   box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -79,6 +86,32 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64
               static_cast<unsigned long long>(row_stride_bytes), box_inner, box_outer);
     return VB200_ERR_CUDA;
   }
+  return VB200_OK;
+}
+
+struct TmapKey {
+  const void* ptr; uint64_t inner, outer, stride; uint32_t box_inner, box_outer; int dtype;
+  bool operator<(const TmapKey& o) const {
+    return std::tie(ptr, inner, outer, stride, box_inner, box_outer, dtype) <
+           std::tie(o.ptr, o.inner, o.outer, o.stride, o.box_inner, o.box_outer, o.dtype);
+  }
+};
+
+int cached_tmap(CUtensorMap* out, vb200_dtype dtype, const void* ptr, uint64_t inner,
+                uint64_t outer, uint64_t stride_bytes, uint32_t box_inner, uint32_t box_outer) {
+  static std::mutex mu;
+  static std::map<TmapKey, CUtensorMap> cache;
+  const TmapKey key{ptr, inner, outer, stride_bytes, box_inner, box_outer, static_cast<int>(dtype)};
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return VB200_OK; }
+  }
+  const int rc = make_tmap_2d(out, dtype, ptr, inner, outer, stride_bytes, box_inner, box_outer);
+  if (rc != VB200_OK) return rc;
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
   return VB200_OK;
 }
 

@@ -1,36 +1,37 @@
 // Non-causal variable-length flash attention, head_dim 64 (reference
 // base.py:112-127 materialises (b, i, j, h) scores + mask + softmax in HBM).
 //
-// One CTA = (utterance, head, 128-query tile); it walks the utterance's keys in blocks of 128.
-//   warp 0 lane 0 : TMA producer  — Q tile once, then K/V blocks through a 2-stage ring
-//   warp 1 lane 0 : MMA issuer    — S = Q K^T      (tcgen05.mma 128x128x16, SS, both K-major)
-//                                   O_blk = P V    (128x64x16, A = P from TMEM (or smem),
-//                                                   B = V straight from the TMA tile, MN-major)
-//   warps 2..5    : softmax       — thread = one query row: tcgen05.ld S, online max/sum in
-//                                   registers, P (bf16) -> TMEM, O_blk added into fp32 registers
-// TMEM: 256 columns per CTA (S 128 | P 64 | O 64), so two CTAs share an SM and one CTA's MMAs
-// overlap the other's exponentials.  Keys past the utterance end are masked to -inf, which is
-// the reference's key-padding mask (base.py:119-124) in the packed-row layout.
+// One CTA = (utterance, head, PAIR of 128-query tiles A/B); it walks the utterance's keys in
+// blocks of 128 and keeps the tensor pipe busy by ping-ponging the two tiles:
+//   warp 0 lane 0 : TMA producer  — Q_A, Q_B once, then K/V blocks through a 3-stage ring
+//   warp 1 lane 0 : MMA issuer    — S_X = Q_X K^T   (tcgen05.mma 128xNx16, SS, both K-major)
+//                                   O_X += P_X V    (128x64x16, A = P_X from TMEM, B = V straight
+//                                                    from the TMA tile as an MN-major operand)
+//   warps 2..5    : softmax of tile A, warps 6..9: softmax of tile B — thread = one query row:
+//                   tcgen05.ld of the 128 scores (max pass, then exp2 pass against a lazily
+//                   updated reference max), P (bf16) written over the S columns in TMEM.
+// O accumulates in TMEM across key blocks (fp32); it is rescaled only when the running max
+// grows by more than 2^8 (exact: the common factor cancels in O / l), so the steady state has no
+// TMEM round trip for O.  While tile A's threads do exponentials the tensor pipe runs tile B's
+// MMAs and vice versa.  TMEM: S_A 128 | S_B 128 | O_A 64 | O_B 64 columns (P_X aliases S_X).
+// Keys past the utterance end are masked to -inf — the reference's key-padding mask
+// (base.py:119-124) in the packed-row layout — and the last key block only issues the MMAs
+// (N resp. K rounded up to 16) its valid keys need.
 #include "common.cuh"
 
 namespace vb200 {
 
-int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
-                uint64_t stride_bytes, uint32_t box_inner, uint32_t box_outer);
-
 namespace attn {
-constexpr int BQ = 128, BKV = 128, HD = 64, KV_STAGES = 2;
+constexpr int BQ = 128, BKV = 128, HD = 64, KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: 128 rows x 128 B
-constexpr int THREADS = 6 * 32;
-constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
-template <bool P_TMEM>
-constexpr int smem_bytes() {
-  return TILE_BYTES * (1 + 2 * KV_STAGES + (P_TMEM ? 0 : 2)) + 1024 + 128;
-}
+constexpr int THREADS = 10 * 32;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_S = 0, COL_O = 256;   // S_X at 128*X, O_X at 256 + 64*X
+constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
+constexpr float RESCALE_LOG2 = 8.0f;
 }  // namespace attn
 
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
       "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -39,34 +40,64 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r
       "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32p(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+        "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]),
+        "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32p(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+      "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+      "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-template <bool P_TMEM>
-__global__ void __launch_bounds__(attn::THREADS, P_TMEM ? 2 : 1) flash_attn_kernel(
+__global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
     const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
     const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
   using namespace attn;
-  const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
+  const int b = blockIdx.z, h = blockIdx.y, qp = blockIdx.x;
   const int row0 = cu_rows[b];
   const int T = cu_rows[b + 1] - row0;
-  if (qt * BQ >= T) return;                       // uniform early exit, before any allocation
+  if (qp * 2 * BQ >= T) return;                   // uniform early exit, before any allocation
+  const bool has_b = qp * 2 * BQ + BQ < T;        // second tile of the pair holds valid rows
   const int nblk = (T + BKV - 1) / BKV;
+  const int last_valid = T - (nblk - 1) * BKV;    // keys inside the utterance in the last block
+  const int last_n = (last_valid + 15) & ~15;     // MMA extent of the last block (multiple of 16)
   const int d = n_heads * HD;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* s_q = smem;
-  uint8_t* s_kv = smem + TILE_BYTES;              // stage s: K at s*2*TILE, V right after
-  uint8_t* s_p = s_kv + 2 * KV_STAGES * TILE_BYTES;   // only when !P_TMEM: two 16 KB K-major tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_p + (P_TMEM ? 0 : 2 * TILE_BYTES));
+  uint8_t* s_q = smem;                            // Q_A, Q_B
+  uint8_t* s_kv = smem + 2 * TILE_BYTES;          // stage s: K at s*2*TILE, V right after
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + 2 * KV_STAGES * TILE_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;                   // [KV_STAGES]
   uint64_t* kv_empty = kv_full + KV_STAGES;       // [KV_STAGES]
-  uint64_t* s_full = kv_empty + KV_STAGES;
-  uint64_t* p_full = s_full + 1;
-  uint64_t* o_full = p_full + 1;
-  uint64_t* o_empty = o_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_empty + 1);
+  uint64_t* s_full = kv_empty + KV_STAGES;        // [2]  S_X(j) complete
+  uint64_t* p_full = s_full + 2;                  // [2]  P_X(j) written (128 arrivals)
+  uint64_t* pv_done = p_full + 2;                 // [2]  O_X += P_X(j) V_j retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -74,10 +105,7 @@ __global__ void __launch_bounds__(attn::THREADS, P_TMEM ? 2 : 1) flash_attn_kern
     tma_prefetch_desc(&tm_qkv);
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 128);
+    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&pv_done[x], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -92,8 +120,9 @@ __global__ void __launch_bounds__(attn::THREADS, P_TMEM ? 2 : 1) flash_attn_kern
   if (warp == 0) {
     if (lane == 0) {
       // ---------------------------------------------------------- TMA producer
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_2d(s_q, &tm_qkv, q_full, h * HD, row0 + qt * BQ);
+      mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
+      tma_load_2d(s_q, &tm_qkv, q_full, h * HD, row0 + qp * 2 * BQ);
+      if (has_b) tma_load_2d(s_q + TILE_BYTES, &tm_qkv, q_full, h * HD, row0 + qp * 2 * BQ + BQ);
       for (int j = 0; j < nblk; ++j) {
         const int s = j % KV_STAGES;
         const uint32_t ph = (j / KV_STAGES) & 1;
@@ -107,166 +136,159 @@ __global__ void __launch_bounds__(attn::THREADS, P_TMEM ? 2 : 1) flash_attn_kern
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV, false, false);
-      constexpr uint32_t idesc_o = umma_idesc_bf16(BQ, HD, false, true);   // B = V, MN-major
-      const uint32_t t_s = tmem_base + COL_S, t_p = tmem_base + COL_P, t_o = tmem_base + COL_O;
-      const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(s_q));
+      const uint32_t idesc_o = umma_idesc_bf16(BQ, HD, false, true);        // B = V, MN-major
+      const int n_tiles = has_b ? 2 : 1;
+      auto issue_s = [&](int x, int j) {      // S_x = Q_x K_j^T
+        const int s = j % KV_STAGES;
+        const int n = (j == nblk - 1) ? last_n : BKV;
+        const uint32_t idesc_s = umma_idesc_bf16(BQ, n, false, false);
+        const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(s_q + x * TILE_BYTES));
+        const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(s_kv + s * 2 * TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_ss(tmem_base + COL_S + x * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[x]);
+      };
+      auto issue_pv = [&](int x, int j) {     // O_x (+)= P_x V_j
+        const int s = j % KV_STAGES;
+        const int ksteps = ((j == nblk - 1) ? last_n : BKV) / 16;
+        const uint32_t sv = smem_u32(s_kv + s * 2 * TILE_BYTES + TILE_BYTES);
+        const uint32_t t_p = tmem_base + COL_S + x * 128;       // P aliases the S columns
+        const uint32_t t_o = tmem_base + COL_O + x * 64;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t dv = umma_desc_mnmajor_sw128(sv + k * 16 * 128, 1024);
+          umma_ts(t_o, t_p + k * 8, dv, idesc_o, (j | k) != 0);
+        }
+        umma_commit(&pv_done[x]);
+      };
       mbar_wait(q_full, 0);
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
-      {
-        const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(s_kv));
-#pragma unroll
-        for (int k = 0; k < HD / 16; ++k) umma_ss(t_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-        umma_commit(s_full);
-      }
+      for (int x = 0; x < n_tiles; ++x) issue_s(x, 0);
       for (int j = 0; j < nblk; ++j) {
-        const int s = j % KV_STAGES;
-        mbar_wait(p_full, j & 1);                       // P_j written, S free
-        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);     // O_blk_{j-1} consumed
-        tc_fence_after();
-        const uint32_t sv = smem_u32(s_kv + s * 2 * TILE_BYTES + TILE_BYTES);
-        if (P_TMEM) {
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            const uint64_t dv = umma_desc_mnmajor_sw128(sv + k * 16 * 128, 1024);
-            umma_ts(t_o, t_p + k * 8, dv, idesc_o, k != 0);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < BKV / 16; ++k) {
-            const uint64_t dp = umma_desc_kmajor_sw128(smem_u32(s_p) + (k / 4) * TILE_BYTES) + 2 * (k % 4);
-            const uint64_t dv = umma_desc_mnmajor_sw128(sv + k * 16 * 128, 1024);
-            umma_ss(t_o, dp, dv, idesc_o, k != 0);
-          }
-        }
-        umma_commit(&kv_empty[s]);                      // K_j / V_j slot free once PV_j retires
-        umma_commit(o_full);
-        if (j + 1 < nblk) {
-          const int s1 = (j + 1) % KV_STAGES;
-          mbar_wait(&kv_full[s1], ((j + 1) / KV_STAGES) & 1);
+        const bool more = j + 1 < nblk;
+        if (more) mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
+        for (int x = 0; x < n_tiles; ++x) {
+          mbar_wait(&p_full[x], j & 1);                  // P_x(j) in TMEM, O_x rescaled if needed
           tc_fence_after();
-          const uint64_t dk = umma_desc_kmajor_sw128(smem_u32(s_kv + s1 * 2 * TILE_BYTES));
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_ss(t_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
+          issue_pv(x, j);
+          if (x == n_tiles - 1) umma_commit(&kv_empty[j % KV_STAGES]);   // K_j / V_j consumed by both tiles
+          if (more) issue_s(x, j + 1);                   // overwrites S_x/P_x(j): ordered after PV_x(j)
         }
       }
     }
   } else {
     // ------------------------------------------------------------ softmax / output warps
-    const int quad = warp & 3;
-    const int r_tile = quad * 32 + lane;               // query row inside the tile
-    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-    const uint32_t t_s = tmem_base + lane_off + COL_S;
-    const uint32_t t_p = tmem_base + lane_off + COL_P;
-    const uint32_t t_o = tmem_base + lane_off + COL_O;
-    float o_acc[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
-    float mx = -INFINITY, l = 0.f, alpha_pending = 0.f;
+    const int x = (warp - 2) >> 2;                     // 0: tile A, 1: tile B
+    if (x == 0 || has_b) {
+      const int quad = warp & 3;
+      const int r_tile = quad * 32 + lane;             // query row inside the tile
+      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+      const uint32_t t_s = tmem_base + lane_off + COL_S + x * 128;
+      const uint32_t t_o = tmem_base + lane_off + COL_O + x * 64;
+      float m_ref = -INFINITY, l = 0.f;
 
-    for (int j = 0; j < nblk; ++j) {
-      mbar_wait(s_full, j & 1);
-      tc_fence_after();
-      const int n_valid = T - j * BKV;                 // keys of this block inside the utterance
-      const bool tail = n_valid < BKV;
-      // pass 1: block max
-      float bm = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_s + c * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float s = __uint_as_float(r[i]);
-          if (tail && c * 32 + i >= n_valid) s = -INFINITY;
-          bm = fmaxf(bm, s);
-        }
-      }
-      const float mx_new = fmaxf(mx, bm);
-      const float alpha = exp2f((mx - mx_new) * scale_log2);   // 0 on the first block
-      const float mneg = -mx_new * scale_log2;
-      float psum = 0.f;
-      // pass 2: P = exp2(s*c - m*c) -> bf16 -> TMEM (or swizzled smem)
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_s + c * 32, r);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(r[i]), scale_log2, mneg));
-          float p1 = exp2f(fmaf(__uint_as_float(r[i + 1]), scale_log2, mneg));
-          if (tail) {
-            if (c * 32 + i >= n_valid) p0 = 0.f;
-            if (c * 32 + i + 1 >= n_valid) p1 = 0.f;
-          }
-          psum += p0 + p1;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        if (P_TMEM) {
-          tmem_st_32x16(t_p + c * 16, pk);
-        } else {
-          // K-major SWIZZLE_128B tile: row r_tile, 16-byte chunk index XOR (row % 8)
-          uint8_t* tile = s_p + (c >> 1) * TILE_BYTES + r_tile * 128;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int chunk = (c & 1) * 4 + q;
-            *reinterpret_cast<uint4*>(tile + ((chunk ^ (r_tile & 7)) << 4)) =
-                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-          }
-        }
-      }
-      if (P_TMEM) tmem_st_wait(); else fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_full);
-      l = l * alpha + psum;
-      mx = mx_new;
-      // fold in the previous block's P V (deferred so this block's exponentials start early)
-      if (j > 0) {
-        mbar_wait(o_full, (j - 1) & 1);
+      for (int j = 0; j < nblk; ++j) {
+        const bool tail = (j == nblk - 1) && last_valid < BKV;
+        const int n_chunks = tail ? (last_n + 31) / 32 : 4;
+        mbar_wait(&s_full[x], j & 1);
         tc_fence_after();
+        // pass 1: row max of this block (two 64-column groups in flight)
+        float bm = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_o + c * 32, r);
-          tmem_ld_wait();
+        for (int g = 0; g < 2; ++g) {
+          if (2 * g < n_chunks) {
+            uint32_t s[64];
+            tmem_ld_32x32p(t_s + g * 64, s);
+            if (2 * g + 1 < n_chunks) tmem_ld_32x32p(t_s + g * 64 + 32, s + 32);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_pending, __uint_as_float(r[i]));
+            for (int i = 0; i < 64; ++i) {
+              float v = __uint_as_float(s[i]);
+              if (tail && g * 64 + i >= last_valid) v = -INFINITY;   // key beyond the utterance
+              bm = fmaxf(bm, v);
+            }
+          }
         }
+        // lazy reference max: rescale O / l only when the max grew by more than 2^8
+        const float grow = (bm - m_ref) * scale_log2;
+        const bool need = grow > RESCALE_LOG2;          // also true on the first block (m_ref = -inf)
+        if (j == 0) {
+          m_ref = bm;
+        } else if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(&pv_done[x], (j - 1) & 1);          // O_x quiescent: PV_x(j-1) retired
+          tc_fence_after();
+          const float alpha = need ? ex2_approx((m_ref - bm) * scale_log2) : 1.0f;
+          if (need) { m_ref = bm; l *= alpha; }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32p(t_o + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32p(t_o + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+        // pass 2: P = exp2(s*c - m_ref*c) -> bf16 -> TMEM, over the S columns already consumed
+        const float mneg = -m_ref * scale_log2;
+        float psum0 = 0.f, psum1 = 0.f;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          if (2 * g < n_chunks) {
+            uint32_t s[64];
+            tmem_ld_32x32p(t_s + g * 64, s);
+            if (2 * g + 1 < n_chunks) tmem_ld_32x32p(t_s + g * 64 + 32, s + 32);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              if (2 * g + c < n_chunks) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i]), scale_log2, mneg));
+                  float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 1]), scale_log2, mneg));
+                  if (tail) {
+                    if (g * 64 + c * 32 + i >= last_valid) p0 = 0.f;
+                    if (g * 64 + c * 32 + i + 1 >= last_valid) p1 = 0.f;
+                  }
+                  psum0 += p0;
+                  psum1 += p1;
+                  pk[i >> 1] = pack_bf16x2(p0, p1);
+                }
+                tmem_st_32x16(t_s + (2 * g + c) * 16, pk);
+              }
+            }
+          }
+        }
+        tmem_st_wait();
         tc_fence_before();
-        mbar_arrive(o_empty);
+        mbar_arrive(&p_full[x]);
+        l += psum0 + psum1;
       }
-      alpha_pending = alpha;
-    }
-    // last block's P V
-    mbar_wait(o_full, (nblk - 1) & 1);
-    tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32(t_o + c * 32, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i)
-        o_acc[c * 32 + i] = fmaf(o_acc[c * 32 + i], alpha_pending, __uint_as_float(r[i]));
-    }
-    const int q_row = qt * BQ + r_tile;
-    if (q_row < T) {
+      // epilogue: O / l -> bf16 rows
+      mbar_wait(&pv_done[x], (nblk - 1) & 1);
+      tc_fence_after();
+      const int q_row = (qp * 2 + x) * BQ + r_tile;
       const float inv = 1.0f / l;
-      __nv_bfloat16* o = out + static_cast<size_t>(row0 + q_row) * d + h * HD;
+      __nv_bfloat16* o_dst = out + static_cast<size_t>(row0 + q_row) * d + h * HD;
 #pragma unroll
-      for (int i = 0; i < HD; i += 8) {
-        uint4 p;
-        p.x = pack_bf16x2(o_acc[i] * inv, o_acc[i + 1] * inv);
-        p.y = pack_bf16x2(o_acc[i + 2] * inv, o_acc[i + 3] * inv);
-        p.z = pack_bf16x2(o_acc[i + 4] * inv, o_acc[i + 5] * inv);
-        p.w = pack_bf16x2(o_acc[i + 6] * inv, o_acc[i + 7] * inv);
-        *reinterpret_cast<uint4*>(o + i) = p;
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32p(t_o + c * 32, o);
+        tmem_ld_wait();
+        if (q_row < T) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            uint4 p;
+            p.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+            p.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+            p.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+            p.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(o_dst + c * 32 + i) = p;
+          }
+        }
       }
     }
   }
@@ -280,35 +302,6 @@ __global__ void __launch_bounds__(attn::THREADS, P_TMEM ? 2 : 1) flash_attn_kern
   }
 }
 
-template <bool P_TMEM>
-static int launch_attn(void* out, const void* qkv, const int32_t* cu_rows, int B, int max_T, int M,
-                       int n_heads, float scale, cudaStream_t st) {
-  using namespace attn;
-  const int d = n_heads * HD;
-  CUtensorMap tm;
-  int rc = cached_tmap(&tm, qkv, static_cast<uint64_t>(3) * d, M, static_cast<uint64_t>(3) * d * 2, HD, 128);
-  if (rc != VB200_OK) return rc;
-  auto kern = flash_attn_kernel<P_TMEM>;
-  static bool configured = false;
-  if (!configured) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<P_TMEM>()));
-    configured = true;
-  }
-  dim3 grid((max_T + BQ - 1) / BQ, n_heads, B);
-  kern<<<grid, THREADS, smem_bytes<P_TMEM>(), st>>>(tm, static_cast<__nv_bfloat16*>(out), cu_rows,
-                                                    n_heads, scale * 1.4426950408889634f);
-  VB_CHECK_CUDA(cudaGetLastError());
-  return VB200_OK;
-}
-
-static int attn_check(void* out, const void* qkv, const int32_t* cu_rows, int B, int max_T, int M,
-                      int n_heads) {
-  VB_REQUIRE(out && qkv && cu_rows, "flash_attn: null pointer");
-  VB_REQUIRE(B >= 1 && B <= 65535 && n_heads >= 1 && n_heads <= 65535 && max_T >= 1 && M >= 0,
-             "flash_attn: bad sizes B=%d heads=%d max_T=%d M=%d", B, n_heads, max_T, M);
-  return VB200_OK;
-}
-
 }  // namespace vb200
 
 using namespace vb200;
@@ -316,21 +309,24 @@ using namespace vb200;
 extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, const int32_t* cu_rows,
                                        int32_t B, int32_t max_T, int32_t M, int32_t n_heads,
                                        float scale, vb200_stream_t stream) {
-  int rc = attn_check(out_bf16, qkv_bf16, cu_rows, B, max_T, M, n_heads);
-  if (rc != VB200_OK) return rc;
+  using namespace attn;
+  VB_REQUIRE(out_bf16 && qkv_bf16 && cu_rows, "flash_attn: null pointer");
+  VB_REQUIRE(B >= 1 && B <= 65535 && n_heads >= 1 && n_heads <= 65535 && max_T >= 1 && M >= 0,
+             "flash_attn: bad sizes B=%d heads=%d max_T=%d M=%d", B, n_heads, max_T, M);
   if (M == 0) return VB200_OK;
-  return launch_attn<true>(out_bf16, qkv_bf16, cu_rows, B, max_T, M, n_heads, scale,
-                           static_cast<cudaStream_t>(stream));
-}
-
-// Bring-up variant: P goes through shared memory (K-major SWIZZLE_128B) instead of TMEM.
-extern "C" int vb200_flash_attn_varlen_psmem(void* out_bf16, const void* qkv_bf16,
-                                             const int32_t* cu_rows, int32_t B, int32_t max_T,
-                                             int32_t M, int32_t n_heads, float scale,
-                                             vb200_stream_t stream) {
-  int rc = attn_check(out_bf16, qkv_bf16, cu_rows, B, max_T, M, n_heads);
+  const int d = n_heads * HD;
+  CUtensorMap tm;
+  int rc = cached_tmap(&tm, VB200_BF16, qkv_bf16, static_cast<uint64_t>(3) * d, M,
+                       static_cast<uint64_t>(3) * d * 2, HD, 128);
   if (rc != VB200_OK) return rc;
-  if (M == 0) return VB200_OK;
-  return launch_attn<false>(out_bf16, qkv_bf16, cu_rows, B, max_T, M, n_heads, scale,
-                            static_cast<cudaStream_t>(stream));
+  static bool configured = false;
+  if (!configured) {
+    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
+  }
+  dim3 grid((max_T + 2 * BQ - 1) / (2 * BQ), n_heads, B);
+  flash_attn_kernel<<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
+      tm, static_cast<__nv_bfloat16*>(out_bf16), cu_rows, n_heads, scale * 1.4426950408889634f);
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
 }

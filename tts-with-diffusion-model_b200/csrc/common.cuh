@@ -29,10 +29,13 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int num_sms();
 
-// Encodes a 2D bf16 row-major tensor map: dims {inner, outer}, box {box_inner, box_outer},
-// SWIZZLE_128B (box_inner * 2 bytes must be 128), zero fill out of bounds.
-int make_tmap_2d_bf16(CUtensorMap* out, const void* gptr, uint64_t inner, uint64_t outer,
-                      uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+// Encodes a 2D row-major tensor map: dims {inner, outer}, box {box_inner, box_outer},
+// SWIZZLE_128B (box_inner * element size must be 128 bytes), zero fill / clipping out of bounds.
+int make_tmap_2d(CUtensorMap* out, vb200_dtype dtype, const void* gptr, uint64_t inner,
+                 uint64_t outer, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+// Same, memoised on (pointer, dtype, shape, box): tensor maps are pure functions of their inputs.
+int cached_tmap(CUtensorMap* out, vb200_dtype dtype, const void* ptr, uint64_t inner,
+                uint64_t outer, uint64_t stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
 // ---------------------------------------------------------------- device PTX wrappers
 #ifdef __CUDACC__
@@ -101,6 +104,32 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)),
       "r"(c_inner), "r"(c_outer)
       : "memory");
+}
+
+// smem tile -> global (bulk async group); out-of-bounds parts of the box are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src,
+                                             int32_t c_inner, int32_t c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c_inner),
+               "r"(c_outer)
+               : "memory");
+}
+// global += smem tile (element-wise add performed at L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* smem_src,
+                                                  int32_t c_inner, int32_t c_outer) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c_inner),
+               "r"(c_outer)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {   // smem source reusable
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() {    // writes complete
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // ---- tcgen05 / TMEM

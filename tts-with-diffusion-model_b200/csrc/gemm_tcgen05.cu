@@ -4,12 +4,14 @@
 // Persistent, warp-specialised sm_100a kernel:
 //   warp 0 lane 0 : TMA producer   (cp.async.bulk.tensor 2D, SWIZZLE_128B, 4-stage ring)
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma cta_group::1 kind::f16, 128x256x16, fp32 in TMEM)
-//   warps 2..9    : epilogue       (tcgen05.ld -> bias / GELU / residual -> global)
+//   warps 2..9    : epilogue       (tcgen05.ld -> bias / GELU -> swizzled smem -> TMA store, or
+//                                   TMA reduce-add into the fp32 residual stream)
 // TMEM holds two 128x256 fp32 accumulators (512 columns) so the epilogue of tile i overlaps the
 // MMAs of tile i+1.  Both operands are K-major (nn.Linear stores W as (N, K)), so no transposes.
-#include <map>
-#include <mutex>
-#include <tuple>
+// Output never leaves the SM through per-thread stores: each epilogue warp writes 32 rows x 128 B
+// into its own SWIZZLE_128B staging tile and one lane hands it to the TMA engine, which clips the
+// M / N tails and, for BIAS_RESIDUAL, performs out += tile at L2 (no read of the residual by SMs).
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -22,7 +24,9 @@ constexpr int B_BYTES = BN * BK * 2;            // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;   // 320
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_TILE_BYTES = 32 * 128;        // 32 rows x 128 B per epilogue warp
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_TILE_BYTES + 1024 /*align slack*/ +
+                           256 /*barriers*/;
 constexpr uint32_t TMEM_COLS = 512;
 }  // namespace gemm
 
@@ -41,14 +45,14 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 template <int EPI, typename OutT>
 __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-    OutT* __restrict__ out, const float* __restrict__ bias, const float* residual, int M, int N,
-    int K) {
+    const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N, int K) {
   using namespace gemm;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
   uint8_t* smem = smem_raw + pad;                      // 1024-byte aligned (SWIZZLE_128B atoms)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;     // EPI_WARPS x 4 KB, each 1024-aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + EPI_WARPS * EPI_TILE_BYTES);
   uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* acc_full = bars + 2 * STAGES;   // [2]     MMA -> epilogue
@@ -63,6 +67,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_out);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * 32); }
     fence_barrier_init();
@@ -124,6 +129,12 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     const int e = warp - 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
     const int half = e >> 2;                   // which 128 of the 256 accumulator columns
+    uint8_t* stage_tile = epi_smem + e * EPI_TILE_BYTES;
+    uint8_t* my_row = stage_tile + lane * 128;
+    const int sw = lane & 7;                   // SWIZZLE_128B: 16-byte chunk index ^= row % 8
+    constexpr bool kWide = sizeof(OutT) == 4;  // fp32: 32 columns per 128-byte row, else 64
+    constexpr int CHUNK_COLS = kWide ? 32 : 64;
+    constexpr int CHUNKS = 128 / CHUNK_COLS;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -131,85 +142,71 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BM + quad * 32 + lane;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
+      const int row0 = m_blk * BM + quad * 32;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * 128;
 #pragma unroll 1
-      for (int c = half * 4; c < half * 4 + 4; ++c) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + c * 32, r);
-        tmem_ld_wait();
-        const int n0 = n_blk * BN + c * 32;
-        if (row < M && n0 < N) {
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int n0 = n_blk * BN + half * 128 + c * CHUNK_COLS;
+        if (lane == 0) tma_store_wait_read();  // previous store has finished reading the staging tile
+        __syncwarp();
+#pragma unroll
+        for (int sub = 0; sub < CHUNK_COLS / 32; ++sub) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_row + c * CHUNK_COLS + sub * 32, r);
+          tmem_ld_wait();
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          const bool full_chunk = (n0 + 32 <= N);
+          const int nb = n0 + sub * 32;
           if (EPI != VB200_EPI_NONE) {
-            if (full_chunk) {
+            if (nb + 32 <= N) {
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + i));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + i));
                 v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
               }
             } else {
-              for (int i = 0; i < 32; ++i) if (n0 + i < N) v[i] += __ldg(bias + n0 + i);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) if (nb + i < N) v[i] += __ldg(bias + nb + i);
             }
           }
           if (EPI == VB200_EPI_BIAS_GELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
           }
-          const size_t off = static_cast<size_t>(row) * N + n0;
-          if (EPI == VB200_EPI_BIAS_RESIDUAL) {
-            if (full_chunk) {
+          if (kWide) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 r4 = *reinterpret_cast<const float4*>(residual + off + i);
-                v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
-              }
-            } else {
-              for (int i = 0; i < 32; ++i) if (n0 + i < N) v[i] += residual[off + i];
-            }
-          }
-          if (sizeof(OutT) == 4) {
-            float* o = reinterpret_cast<float*>(out) + off;
-            if (full_chunk) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4)
-                *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            } else {
-              for (int i = 0; i < 32; ++i) if (n0 + i < N) o[i] = v[i];
-            }
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(my_row + ((q ^ sw) << 4)) =
+                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           } else {
-            uint16_t* o = reinterpret_cast<uint16_t*>(out) + off;
             constexpr bool is_bf16 = std::is_same<OutT, __nv_bfloat16>::value;
-            if (full_chunk) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 8) {
-                uint4 p;
-                if (is_bf16) {
-                  p.x = pack_bf16x2(v[i], v[i + 1]); p.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                  p.z = pack_bf16x2(v[i + 4], v[i + 5]); p.w = pack_bf16x2(v[i + 6], v[i + 7]);
-                } else {
-                  p.x = pack_f16x2(v[i], v[i + 1]); p.y = pack_f16x2(v[i + 2], v[i + 3]);
-                  p.z = pack_f16x2(v[i + 4], v[i + 5]); p.w = pack_f16x2(v[i + 6], v[i + 7]);
-                }
-                *reinterpret_cast<uint4*>(o + i) = p;
+            for (int q = 0; q < 4; ++q) {
+              uint4 p;
+              if (is_bf16) {
+                p.x = pack_bf16x2(v[8 * q], v[8 * q + 1]); p.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+                p.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]); p.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+              } else {
+                p.x = pack_f16x2(v[8 * q], v[8 * q + 1]); p.y = pack_f16x2(v[8 * q + 2], v[8 * q + 3]);
+                p.z = pack_f16x2(v[8 * q + 4], v[8 * q + 5]); p.w = pack_f16x2(v[8 * q + 6], v[8 * q + 7]);
               }
-            } else {
-              for (int i = 0; i < 32; ++i) {
-                if (n0 + i < N) {
-                  if (is_bf16) { __nv_bfloat16 h = __float2bfloat16_rn(v[i]); o[i] = *reinterpret_cast<uint16_t*>(&h); }
-                  else { __half h = __float2half_rn(v[i]); o[i] = *reinterpret_cast<uint16_t*>(&h); }
-                }
-              }
+              *reinterpret_cast<uint4*>(my_row + (((sub * 4 + q) ^ sw) << 4)) = p;
             }
           }
+        }
+        fence_proxy_async_smem();              // generic-proxy smem writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0 && row0 < M && n0 < N) {
+          if (EPI == VB200_EPI_BIAS_RESIDUAL) tma_reduce_add_2d(&tm_out, stage_tile, n0, row0);
+          else tma_store_2d(&tm_out, stage_tile, n0, row0);
+          tma_store_commit();
         }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -222,37 +219,9 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
 }
 
 // ---------------------------------------------------------------- host side
-struct TmapKey {
-  const void* ptr; uint64_t inner, outer, stride; uint32_t box_outer;
-  bool operator<(const TmapKey& o) const {
-    return std::tie(ptr, inner, outer, stride, box_outer) <
-           std::tie(o.ptr, o.inner, o.outer, o.stride, o.box_outer);
-  }
-};
-
-// Tensor maps are pure functions of (pointer, shape, box); cache them so steady-state launches
-// (and CUDA-graph re-captures) do not re-encode.
-int cached_tmap(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer,
-                uint64_t stride_bytes, uint32_t box_inner, uint32_t box_outer) {
-  static std::mutex mu;
-  static std::map<TmapKey, CUtensorMap> cache;
-  const TmapKey key{ptr, inner, outer, stride_bytes, box_outer};
-  {
-    std::lock_guard<std::mutex> g(mu);
-    auto it = cache.find(key);
-    if (it != cache.end()) { *out = it->second; return VB200_OK; }
-  }
-  const int rc = make_tmap_2d_bf16(out, ptr, inner, outer, stride_bytes, box_inner, box_outer);
-  if (rc != VB200_OK) return rc;
-  std::lock_guard<std::mutex> g(mu);
-  if (cache.size() > 4096) cache.clear();
-  cache[key] = *out;
-  return VB200_OK;
-}
-
 template <int EPI, typename OutT>
-static int launch_gemm(void* out, const CUtensorMap& ta, const CUtensorMap& tb, const float* bias,
-                       const float* residual, int M, int N, int K, cudaStream_t st) {
+static int launch_gemm(void* out, vb200_dtype dt, const CUtensorMap& ta, const CUtensorMap& tb,
+                       const float* bias, int M, int N, int K, cudaStream_t st) {
   using namespace gemm;
   auto kern = gemm_tcgen05_kernel<EPI, OutT>;
   static bool configured = false;   // per template instantiation
@@ -260,21 +229,24 @@ static int launch_gemm(void* out, const CUtensorMap& ta, const CUtensorMap& tb, 
     VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
+  CUtensorMap tout;   // store box: 32 rows x 128 bytes
+  const int esz = sizeof(OutT);
+  int rc = cached_tmap(&tout, dt, out, N, M, static_cast<uint64_t>(N) * esz, 128 / esz, 32);
+  if (rc != VB200_OK) return rc;
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, THREADS, SMEM_BYTES, st>>>(ta, tb, static_cast<OutT*>(out), bias, residual, M, N, K);
+  kern<<<grid, THREADS, SMEM_BYTES, st>>>(ta, tb, tout, bias, M, N, K);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
 
 template <int EPI>
 static int launch_gemm_dtype(void* out, vb200_dtype dt, const CUtensorMap& ta, const CUtensorMap& tb,
-                             const float* bias, const float* residual, int M, int N, int K,
-                             cudaStream_t st) {
+                             const float* bias, int M, int N, int K, cudaStream_t st) {
   switch (dt) {
-    case VB200_F32: return launch_gemm<EPI, float>(out, ta, tb, bias, residual, M, N, K, st);
-    case VB200_BF16: return launch_gemm<EPI, __nv_bfloat16>(out, ta, tb, bias, residual, M, N, K, st);
-    case VB200_F16: return launch_gemm<EPI, __half>(out, ta, tb, bias, residual, M, N, K, st);
+    case VB200_F32: return launch_gemm<EPI, float>(out, dt, ta, tb, bias, M, N, K, st);
+    case VB200_BF16: return launch_gemm<EPI, __nv_bfloat16>(out, dt, ta, tb, bias, M, N, K, st);
+    case VB200_F16: return launch_gemm<EPI, __half>(out, dt, ta, tb, bias, M, N, K, st);
   }
   set_error("gemm: unknown out dtype %d", static_cast<int>(dt));
   return VB200_ERR_INVALID;
@@ -297,16 +269,21 @@ extern "C" int vb200_gemm_bf16(void* out, vb200_dtype out_dtype, const void* A, 
              "gemm: BIAS_RESIDUAL needs residual and fp32 output");
   if (M == 0) return VB200_OK;
   CUtensorMap ta, tb;
-  int rc = cached_tmap(&ta, A, K, M, static_cast<uint64_t>(K) * 2, gemm::BK, gemm::BM);
+  int rc = cached_tmap(&ta, VB200_BF16, A, K, M, static_cast<uint64_t>(K) * 2, gemm::BK, gemm::BM);
   if (rc != VB200_OK) return rc;
-  rc = cached_tmap(&tb, W, K, N, static_cast<uint64_t>(K) * 2, gemm::BK, gemm::BN);
+  rc = cached_tmap(&tb, VB200_BF16, W, K, N, static_cast<uint64_t>(K) * 2, gemm::BK, gemm::BN);
   if (rc != VB200_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epi) {
-    case VB200_EPI_NONE: return launch_gemm_dtype<VB200_EPI_NONE>(out, out_dtype, ta, tb, bias, residual, M, N, K, st);
-    case VB200_EPI_BIAS: return launch_gemm_dtype<VB200_EPI_BIAS>(out, out_dtype, ta, tb, bias, residual, M, N, K, st);
-    case VB200_EPI_BIAS_GELU: return launch_gemm_dtype<VB200_EPI_BIAS_GELU>(out, out_dtype, ta, tb, bias, residual, M, N, K, st);
-    case VB200_EPI_BIAS_RESIDUAL: return launch_gemm<VB200_EPI_BIAS_RESIDUAL, float>(out, ta, tb, bias, residual, M, N, K, st);
+    case VB200_EPI_NONE: return launch_gemm_dtype<VB200_EPI_NONE>(out, out_dtype, ta, tb, bias, M, N, K, st);
+    case VB200_EPI_BIAS: return launch_gemm_dtype<VB200_EPI_BIAS>(out, out_dtype, ta, tb, bias, M, N, K, st);
+    case VB200_EPI_BIAS_GELU: return launch_gemm_dtype<VB200_EPI_BIAS_GELU>(out, out_dtype, ta, tb, bias, M, N, K, st);
+    case VB200_EPI_BIAS_RESIDUAL:
+      // out (+)= acc + bias is a TMA reduce-add into `out`; a distinct residual is copied in first
+      if (residual != static_cast<const float*>(out))
+        VB_CHECK_CUDA(cudaMemcpyAsync(out, residual, static_cast<size_t>(M) * N * sizeof(float),
+                                      cudaMemcpyDeviceToDevice, st));
+      return launch_gemm<VB200_EPI_BIAS_RESIDUAL, float>(out, out_dtype, ta, tb, bias, M, N, K, st);
   }
   set_error("gemm: unknown epilogue %d", static_cast<int>(epi));
   return VB200_ERR_INVALID;

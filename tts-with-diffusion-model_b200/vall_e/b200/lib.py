@@ -38,7 +38,6 @@ PROTOTYPES = {
     "vb200_gemm_bf16": ([_p, C.c_int, _p, _p, _p, _p, _i32, _i32, _i32, C.c_int, _p], C.c_int),
     "vb200_gemm_bf16_simt": ([_p, C.c_int, _p, _p, _p, _p, _i32, _i32, _i32, C.c_int, _p], C.c_int),
     "vb200_flash_attn_varlen": ([_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p], C.c_int),
-    "vb200_flash_attn_varlen_psmem": ([_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p], C.c_int),
     "vb200_attn_varlen_simt": ([_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p], C.c_int),
     "vb200_q_sample": ([_p] * 6 + [_i32, _i32, _i32, C.c_int, _p], C.c_int),
     "vb200_posterior_sample_from_logits": (
@@ -140,8 +139,7 @@ def gemm_bf16(out, A, W, bias=None, residual=None, epi=EPI_NONE, simt=False):
 def flash_attn_varlen(out, qkv, cu_rows, max_T, n_heads, scale, variant="tmem"):
     M = qkv.shape[0]
     B = cu_rows.numel() - 1
-    fn = {"tmem": load().vb200_flash_attn_varlen, "psmem": load().vb200_flash_attn_varlen_psmem,
-          "simt": load().vb200_attn_varlen_simt}[variant]
+    fn = {"tmem": load().vb200_flash_attn_varlen, "simt": load().vb200_attn_varlen_simt}[variant]
     _check(fn(ptr(out), ptr(qkv), ptr(cu_rows), B, max_T, M, n_heads, scale, stream()),
            f"vb200_flash_attn_varlen[{variant}]")
 
