@@ -28,6 +28,11 @@ struct Philox {
   }
 };
 __device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * 5.9604644775390625e-8f; }
+__device__ __forceinline__ float exp2f_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Gumbel noise exactly as the reference forms it, evaluated through double so that each fp32
 // log is correctly rounded (the CPU reference's SLEEF logf is <= 1 ulp; agreeing with the
@@ -274,6 +279,173 @@ __global__ void __launch_bounds__(256) posterior_sample_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------- P, production form
+// Register-resident O(K) reverse step for K = 256*KC (<= 1024): one warp per token, the K logits
+// are read from HBM exactly once (16-byte loads), softmax statistics stay in registers, and the
+// token is drawn by inverse CDF from ONE Philox uniform — an exact categorical sample, equal in
+// distribution to the reference's Gumbel-max over K uniforms (ar_discrete.py:402-419) at 1/K of
+// the random numbers and no per-class logarithm.
+//
+// With e_j = exp(l_j - max), Z = sum e_j, p_j = e_j / Z the unnormalised posterior weight is
+//   w_j = (f1_j + eps) (f2_j + eps),  f2_j + eps = p_j (a_j - c_j) + c_j + eps.
+// Every class except x_t (and the absorbing class m) shares f1 / a / c, so
+//   sum_j w_j = coef * Z + K * cst  (+ non-negative corrections dx, dm for the special classes)
+// is closed form; the per-class weights are only walked when the draw lands in the generic part.
+// Greedy mode (argmax of the same weights) needs no logarithm either.
+template <typename T, int KC, int NOISE>
+__global__ void __launch_bounds__(256) posterior_fast_kernel(
+    int32_t* __restrict__ x_out, const T* __restrict__ logits, int64_t ld_logits,
+    const int32_t* __restrict__ x_t_all, const int32_t* __restrict__ row_utt,
+    const int32_t* __restrict__ t_utt, const int32_t* __restrict__ utt,
+    const float* __restrict__ table, int n_rows, int n_levels, int S, int transition,
+    uint32_t seed_lo, uint32_t seed_hi) {
+  constexpr int K = KC * 256;
+  constexpr int NR = KC * 8;                  // logits per lane
+  constexpr float kLog2e = 1.4426950408889634f;
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tok = n_rows * n_levels;
+  for (int tok = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tok < n_tok;
+       tok += gridDim.x * warps_per_block) {
+    const int row = tok / n_levels, level = tok - row * n_levels;
+    const int b = row_utt[row];
+    const int t = min(max(t_utt[b], 0), S - 1);
+    const T* lrow = logits + static_cast<size_t>(row) * ld_logits + static_cast<size_t>(level) * K;
+    // lane owns classes j = c*256 + lane*8 + i  (c < KC, i < 8) in registers v[c*8 + i]
+    float v[NR];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+      float tmp[8];
+      load8<T>(lrow + c * 256 + lane * 8, tmp);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[c * 8 + i] = tmp[i];
+    }
+    // argmax of the logits (lowest index wins ties) and row max
+    Best top{-INFINITY, 0x7fffffff};
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int j = (r >> 3) * 256 + lane * 8 + (r & 7);
+      if (v[r] > top.v) { top.v = v[r]; top.j = j; }     // ascending j inside a lane
+    }
+    top = warp_best(top);
+    const float mx = top.v;
+    if (t == 0) {                                         // raw logits, no noise (ar_discrete.py:407,413)
+      if (lane == 0) x_out[tok] = top.j;
+      continue;
+    }
+    float part[KC];                                       // per-lane partial sums of e_j, one per 8-chunk
+    float lane_sum = 0.f;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float e = exp2f_fast((v[c * 8 + i] - mx) * kLog2e);
+        v[c * 8 + i] = e;
+        acc += e;
+      }
+      part[c] = acc;
+      lane_sum += acc;
+    }
+    // inclusive warp scan of the lane sums (class order of the CDF = lane-major, any fixed order works)
+    float incl = lane_sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float n = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += n;
+    }
+    const float Z = __shfl_sync(0xffffffffu, incl, 31);
+    const float invZ = 1.0f / Z;
+
+    const int t1 = t - 1;
+    const float* one = table + static_cast<size_t>(t) * VB200_TAB_STRIDE;
+    const float* cum = table + static_cast<size_t>(t1) * VB200_TAB_STRIDE;
+    const int x_t = x_t_all[tok];
+    const bool absorbing = transition == VB200_ABSORBING;
+    const int m = absorbing ? K / 2 : -1;
+    const bool at_m = x_t == m;
+    const float f1_self = (absorbing ? (at_m ? one[VB200_TAB_ONE_BOTH] : one[VB200_TAB_ONE_KEEP]) : one[VB200_TAB_ONE_KEEP]) + kEps;
+    const float f1_oth = (absorbing ? (at_m ? one[VB200_TAB_ONE_ABSORB] : one[VB200_TAB_ONE_OFF]) : one[VB200_TAB_ONE_OFF]) + kEps;
+    const float a_gen = cum[VB200_TAB_CUM_KEEP], c_gen = cum[VB200_TAB_CUM_OFF];
+    const float a_m = absorbing ? cum[VB200_TAB_CUM_BOTH] : a_gen, c_m = absorbing ? cum[VB200_TAB_CUM_ABSORB] : c_gen;
+    // generic class: w_j = coef * e_j + cst
+    const float coef = (a_gen - c_gen) * invZ * f1_oth;
+    const float cst = (c_gen + kEps) * f1_oth;
+    // special classes: true weight minus what the generic formula assigns them (>= 0)
+    const float e_x = exp2f_fast((load_logit<T>(lrow, x_t) - mx) * kLog2e);
+    const float ax = at_m ? a_m : a_gen, cx = at_m ? c_m : c_gen;
+    const float w_x = f1_self * (fmaf(e_x * invZ, ax - cx, cx) + kEps);
+    const float dx = fmaxf(w_x - fmaf(e_x, coef, cst), 0.f);
+    float w_m = 0.f, dm = 0.f;
+    if (absorbing && !at_m) {
+      const float e_m = exp2f_fast((load_logit<T>(lrow, m) - mx) * kLog2e);
+      w_m = f1_oth * (fmaf(e_m * invZ, a_m - c_m, c_m) + kEps);
+      dm = fmaxf(w_m - fmaf(e_m, coef, cst), 0.f);
+    }
+    int pick;
+    if (NOISE == VB200_NOISE_GREEDY) {
+      // generic weights are monotone in the logit, special classes only gain: compare three candidates
+      float best_w = fmaf(exp2f_fast((top.v - mx) * kLog2e), coef, cst);
+      pick = top.j;
+      if (top.j == x_t) best_w = w_x;
+      else if (top.j == m) best_w = w_m;
+      if (w_x > best_w || (w_x == best_w && x_t < pick)) { best_w = w_x; pick = x_t; }
+      if (absorbing && !at_m && (w_m > best_w || (w_m == best_w && m < pick))) { best_w = w_m; pick = m; }
+    } else {
+      const int32_t* ur = utt + static_cast<size_t>(b) * VB200_U_STRIDE;
+      const uint32_t gid = static_cast<uint32_t>(ur[VB200_U_GID]);
+      const uint32_t frame = static_cast<uint32_t>(row - ur[VB200_U_RESP0]);
+      const Philox ph{seed_lo, seed_hi};
+      const uint4 rnd = ph(0xC0DEu, frame * n_levels + level, gid, t);
+      const float w_generic = fmaf(coef, Z, static_cast<float>(K) * cst);
+      float target = u01(rnd.x) * (w_generic + dx + dm);
+      if (target < dx) {
+        pick = x_t;
+      } else if (target < dx + dm) {
+        pick = m;
+      } else {
+        target -= dx + dm;
+        // lane-level CDF of the generic weights: lane sum = coef * sum(e) + NR * cst
+        const float w_incl = fmaf(coef, incl, static_cast<float>((lane + 1) * NR) * cst);
+        const unsigned ball = __ballot_sync(0xffffffffu, target < w_incl);
+        const int src = ball ? __ffs(ball) - 1 : 31;      // rounding at the top end -> last lane
+        const float base = __shfl_sync(0xffffffffu, w_incl - fmaf(coef, lane_sum, static_cast<float>(NR) * cst), src);
+        int local = K - 1;
+        if (lane == src) {
+          float run = base;                                // cumulative weight before this lane
+          int c_sel = KC - 1;
+          bool done = false;
+#pragma unroll
+          for (int c = 0; c < KC - 1; ++c) {               // which 8-class chunk
+            const float nxt = run + fmaf(coef, part[c], 8.0f * cst);
+            if (!done) {
+              if (target < nxt) { c_sel = c; done = true; }
+              else run = nxt;
+            }
+          }
+          int i_sel = 7;                                   // rounding at the top end -> last class
+#pragma unroll
+          for (int c = 0; c < KC; ++c) {
+            if (c == c_sel) {
+              float r2 = run;
+              bool found = false;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                r2 += fmaf(coef, v[c * 8 + i], cst);
+                if (!found && target < r2) { found = true; i_sel = i; }
+              }
+            }
+          }
+          local = c_sel * 256 + lane * 8 + i_sel;
+        }
+        pick = __shfl_sync(0xffffffffu, local, src);
+      }
+    }
+    if (lane == 0) x_out[tok] = pick;
+  }
+}
+
 template <typename T>
 static int launch_posterior(int32_t* x_out, float* post_out, const void* logits, int64_t ld,
                             const int32_t* x_t, const int32_t* row_utt, const int32_t* t_utt,
@@ -286,6 +458,26 @@ static int launch_posterior(int32_t* x_out, float* post_out, const void* logits,
   const int cap = num_sms() * 8 * 4;
   if (grid > cap) grid = cap;
   const uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
+  // production form: register-resident, single read of the logits (see posterior_fast_kernel)
+  const bool aligned = (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  if (!post_out && aligned && noise != VB200_NOISE_UNIFORMS && K % 256 == 0 && K <= 1024) {
+    const T* lg = static_cast<const T*>(logits);
+#define VB_LAUNCH_F(KC, NZ)                                                                      \
+  posterior_fast_kernel<T, KC, NZ><<<grid, wpb * 32, 0, st>>>(x_out, lg, ld, x_t, row_utt, t_utt, \
+                                                             utt, table, n_rows, n_levels, S, tr, lo, hi)
+#define VB_LAUNCH_FK(NZ)                                              \
+  switch (K / 256) {                                                  \
+    case 1: VB_LAUNCH_F(1, NZ); break;                                \
+    case 2: VB_LAUNCH_F(2, NZ); break;                                \
+    case 3: VB_LAUNCH_F(3, NZ); break;                                \
+    default: VB_LAUNCH_F(4, NZ); break;                               \
+  }
+    if (noise == VB200_NOISE_GREEDY) { VB_LAUNCH_FK(VB200_NOISE_GREEDY) } else { VB_LAUNCH_FK(VB200_NOISE_PHILOX) }
+#undef VB_LAUNCH_FK
+#undef VB_LAUNCH_F
+    VB_CHECK_CUDA(cudaGetLastError());
+    return VB200_OK;
+  }
 #define VB_LAUNCH_P(NZ)                                                                        \
   posterior_sample_kernel<T, NZ><<<grid, wpb * 32, 0, st>>>(                                   \
       x_out, post_out, static_cast<const T*>(logits), ld, x_t, row_utt, t_utt, utt, table,     \
