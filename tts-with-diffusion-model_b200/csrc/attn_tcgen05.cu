@@ -71,6 +71,96 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// One key block of one query tile, executed by the 128 threads that own the tile's rows.
+// TAIL = this is the utterance's last block and some of its keys lie beyond the utterance end.
+template <bool TAIL>
+__device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_o, uint64_t* pv_done_x, int j,
+                                              int n_chunks, int last_valid, float scale_log2,
+                                              float& m_ref, float& l) {
+  using namespace attn;
+  // pass 1: row max of this block (64-column groups, four independent max chains)
+  float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {
+    if (!TAIL || 2 * g < n_chunks) {
+      uint32_t s[64];
+      tmem_ld_32x32p(t_s + g * 64, s);
+      if (!TAIL || 2 * g + 1 < n_chunks) tmem_ld_32x32p(t_s + g * 64 + 32, s + 32);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) {
+        float v0 = __uint_as_float(s[i]), v1 = __uint_as_float(s[i + 1]);
+        float v2 = __uint_as_float(s[i + 2]), v3 = __uint_as_float(s[i + 3]);
+        if (TAIL) {                                        // key beyond the utterance
+          if (g * 64 + i >= last_valid) v0 = -INFINITY;
+          if (g * 64 + i + 1 >= last_valid) v1 = -INFINITY;
+          if (g * 64 + i + 2 >= last_valid) v2 = -INFINITY;
+          if (g * 64 + i + 3 >= last_valid) v3 = -INFINITY;
+        }
+        bm0 = fmaxf(bm0, v0); bm1 = fmaxf(bm1, v1); bm2 = fmaxf(bm2, v2); bm3 = fmaxf(bm3, v3);
+      }
+    }
+  }
+  const float bm = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
+  // lazy reference max: rescale O / l only when the max grew by more than 2^8
+  const bool need = (bm - m_ref) * scale_log2 > RESCALE_LOG2;   // also true on the first block
+  if (j == 0) {
+    m_ref = bm;
+  } else if (__any_sync(0xffffffffu, need)) {
+    mbar_wait(pv_done_x, (j - 1) & 1);                    // O_x quiescent: PV_x(j-1) retired
+    tc_fence_after();
+    const float alpha = need ? ex2_approx((m_ref - bm) * scale_log2) : 1.0f;
+    if (need) { m_ref = bm; l *= alpha; }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32p(t_o + c * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st_32x32p(t_o + c * 32, o);
+    }
+    tmem_st_wait();
+  }
+  // pass 2: P = exp2(s*c - m_ref*c) -> bf16 -> TMEM, over the S columns already consumed
+  const float mneg = -m_ref * scale_log2;
+  float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {
+    if (!TAIL || 2 * g < n_chunks) {
+      uint32_t s[64];
+      tmem_ld_32x32p(t_s + g * 64, s);
+      if (!TAIL || 2 * g + 1 < n_chunks) tmem_ld_32x32p(t_s + g * 64 + 32, s + 32);
+      tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (!TAIL || 2 * g + c < n_chunks) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i]), scale_log2, mneg));
+            float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 1]), scale_log2, mneg));
+            float p2 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 2]), scale_log2, mneg));
+            float p3 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 3]), scale_log2, mneg));
+            if (TAIL) {
+              const int k0 = g * 64 + c * 32 + i;
+              if (k0 >= last_valid) p0 = 0.f;
+              if (k0 + 1 >= last_valid) p1 = 0.f;
+              if (k0 + 2 >= last_valid) p2 = 0.f;
+              if (k0 + 3 >= last_valid) p3 = 0.f;
+            }
+            ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+            pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          }
+          tmem_st_32x16(t_s + (2 * g + c) * 16, pk);
+        }
+      }
+    }
+  }
+  l += (ps0 + ps1) + (ps2 + ps3);
+}
+
 __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
     const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
     const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
@@ -190,82 +280,13 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
 
       for (int j = 0; j < nblk; ++j) {
         const bool tail = (j == nblk - 1) && last_valid < BKV;
-        const int n_chunks = tail ? (last_n + 31) / 32 : 4;
         mbar_wait(&s_full[x], j & 1);
         tc_fence_after();
-        // pass 1: row max of this block (two 64-column groups in flight)
-        float bm = -INFINITY;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (2 * g < n_chunks) {
-            uint32_t s[64];
-            tmem_ld_32x32p(t_s + g * 64, s);
-            if (2 * g + 1 < n_chunks) tmem_ld_32x32p(t_s + g * 64 + 32, s + 32);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 64; ++i) {
-              float v = __uint_as_float(s[i]);
-              if (tail && g * 64 + i >= last_valid) v = -INFINITY;   // key beyond the utterance
-              bm = fmaxf(bm, v);
-            }
-          }
-        }
-        // lazy reference max: rescale O / l only when the max grew by more than 2^8
-        const float grow = (bm - m_ref) * scale_log2;
-        const bool need = grow > RESCALE_LOG2;          // also true on the first block (m_ref = -inf)
-        if (j == 0) {
-          m_ref = bm;
-        } else if (__any_sync(0xffffffffu, need)) {
-          mbar_wait(&pv_done[x], (j - 1) & 1);          // O_x quiescent: PV_x(j-1) retired
-          tc_fence_after();
-          const float alpha = need ? ex2_approx((m_ref - bm) * scale_log2) : 1.0f;
-          if (need) { m_ref = bm; l *= alpha; }
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32p(t_o + c * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st_32x32p(t_o + c * 32, o);
-          }
-          tmem_st_wait();
-        }
-        // pass 2: P = exp2(s*c - m_ref*c) -> bf16 -> TMEM, over the S columns already consumed
-        const float mneg = -m_ref * scale_log2;
-        float psum0 = 0.f, psum1 = 0.f;
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          if (2 * g < n_chunks) {
-            uint32_t s[64];
-            tmem_ld_32x32p(t_s + g * 64, s);
-            if (2 * g + 1 < n_chunks) tmem_ld_32x32p(t_s + g * 64 + 32, s + 32);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              if (2 * g + c < n_chunks) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                  float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i]), scale_log2, mneg));
-                  float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 1]), scale_log2, mneg));
-                  if (tail) {
-                    if (g * 64 + c * 32 + i >= last_valid) p0 = 0.f;
-                    if (g * 64 + c * 32 + i + 1 >= last_valid) p1 = 0.f;
-                  }
-                  psum0 += p0;
-                  psum1 += p1;
-                  pk[i >> 1] = pack_bf16x2(p0, p1);
-                }
-                tmem_st_32x16(t_s + (2 * g + c) * 16, pk);
-              }
-            }
-          }
-        }
+        if (!tail) softmax_block<false>(t_s, t_o, &pv_done[x], j, 4, BKV, scale_log2, m_ref, l);
+        else softmax_block<true>(t_s, t_o, &pv_done[x], j, (last_n + 31) / 32, last_valid, scale_log2, m_ref, l);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[x]);
-        l += psum0 + psum1;
       }
       // epilogue: O / l -> bf16 rows
       mbar_wait(&pv_done[x], (nblk - 1) & 1);
