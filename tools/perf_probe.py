@@ -48,7 +48,34 @@ def attn(lens, heads, variant):
     print(f"attn[{variant}] B={len(lens)} T={lens[0]} heads={heads}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s", flush=True)
 
 
+def small_kernels():
+    sys.path.insert(0, str(ROOT / "tts-with-diffusion-model_b200"))
+    from vall_e.vall_e import d3pm
+    M, d = 262912, 1024
+    x = torch.randn(M, d, device=dev)
+    table = torch.randn(52, 2 * d, device=dev)
+    out = torch.empty(M, d, dtype=torch.bfloat16, device=dev)
+    lv = torch.full((256,), 7, dtype=torch.int32, device=dev)
+    ru = torch.arange(256, dtype=torch.int32, device=dev).repeat_interleave(1027)
+    ms = timeit(lambda: L.adaln(out, x, table, lv, ru))
+    print(f"adaln M={M} d={d}: {ms:.3f} ms {M*d*6/ms/1e6:.0f} GB/s", flush=True)
+    S, K, rows = 51, 1024, 192000
+    tab = d3pm.scalar_table(S, K, "absorbing").to(dev)
+    logits = torch.randn(rows, 8 * K, device=dev).half()
+    x_t = torch.full((rows, 8), K // 2, dtype=torch.int32, device=dev)
+    row_utt = torch.arange(256, dtype=torch.int32, device=dev).repeat_interleave(750)
+    utt = torch.zeros(256, L.U_STRIDE, dtype=torch.int32, device=dev)
+    utt[:, L.U_RESP0] = torch.arange(256, device=dev, dtype=torch.int32) * 750
+    t_utt = torch.full((256,), 30, dtype=torch.int32, device=dev)
+    o = torch.empty(rows, 8, dtype=torch.int32, device=dev)
+    for name, mode in (("philox-icdf", L.NOISE_PHILOX), ("greedy", L.NOISE_GREEDY)):
+        ms = timeit(lambda: L.posterior_sample_from_logits(o, None, logits, 8 * K, x_t, row_utt, t_utt, utt, tab, rows, 8,
+                                                           K, L.ABSORBING, mode, seed=1), iters=5)
+        print(f"posterior[{name}] tokens={rows*8}: {ms:.3f} ms {rows*8*(2*K+8)/ms/1e6:.0f} GB/s", flush=True)
+
+
 if __name__ == "__main__":
+    small_kernels()
     for B in (1, 32):
         M = 1027 * B
         gemm(M, 3072, 1024, L.EPI_NONE, torch.bfloat16)

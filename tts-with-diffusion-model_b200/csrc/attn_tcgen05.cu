@@ -8,12 +8,13 @@
 //                                   O_X += P_X V    (128x64x16, A = P_X from TMEM, B = V straight
 //                                                    from the TMA tile as an MN-major operand)
 //   warps 2..5    : softmax of tile A, warps 6..9: softmax of tile B — thread = one query row:
-//                   tcgen05.ld of the 128 scores (max pass, then exp2 pass against a lazily
-//                   updated reference max), P (bf16) written over the S columns in TMEM.
+//                   one tcgen05.ld pass of the 128 scores per block: exp2 against a reference max
+//                   carried over from earlier blocks (exact max pass only for block 0), P (bf16)
+//                   written to its own TMEM columns, so S_X(j+1) can be issued before P_X(j) V_j.
 // O accumulates in TMEM across key blocks (fp32); it is rescaled only when the running max
 // grows by more than 2^8 (exact: the common factor cancels in O / l), so the steady state has no
 // TMEM round trip for O.  While tile A's threads do exponentials the tensor pipe runs tile B's
-// MMAs and vice versa.  TMEM: S_A 128 | S_B 128 | O_A 64 | O_B 64 columns (P_X aliases S_X).
+// MMAs and vice versa.  TMEM (512 columns): S_A 128 | S_B 128 | P_A 64 | P_B 64 | O_A 64 | O_B 64.
 // Keys past the utterance end are masked to -inf — the reference's key-padding mask
 // (base.py:119-124) in the packed-row layout — and the last key block only issues the MMAs
 // (N resp. K rounded up to 16) its valid keys need.
@@ -26,7 +27,7 @@ constexpr int BQ = 128, BKV = 128, HD = 64, KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: 128 rows x 128 B
 constexpr int THREADS = 10 * 32;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_S = 0, COL_O = 256;   // S_X at 128*X, O_X at 256 + 64*X
+constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;   // S_X at 128*X, P_X at 256+64*X, O_X at 384+64*X
 constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
 constexpr float RESCALE_LOG2 = 8.0f;
 }  // namespace attn
@@ -71,14 +72,57 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// One key block of one query tile, executed by the 128 threads that own the tile's rows.
-// TAIL = this is the utterance's last block and some of its keys lie beyond the utterance end.
+// 32 scores of one row -> 32 probabilities (bf16, 16 TMEM columns); max / sum tracked on 4 chains.
 template <bool TAIL>
-__device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_o, uint64_t* pv_done_x, int j,
-                                              int n_chunks, int last_valid, float scale_log2,
-                                              float& m_ref, float& l) {
-  using namespace attn;
-  // pass 1: row max of this block (64-column groups, four independent max chains)
+__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint32_t t_p_chunk, int k_base,
+                                          int last_valid, float scale_log2, float mneg,
+                                          float (&bm)[4], float (&ps)[4]) {
+  uint32_t pk[16];
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float v0 = __uint_as_float(s[i]), v1 = __uint_as_float(s[i + 1]);
+    float v2 = __uint_as_float(s[i + 2]), v3 = __uint_as_float(s[i + 3]);
+    if (TAIL) {                                    // key beyond the utterance: exp2(-inf) = 0
+      if (k_base + i >= last_valid) v0 = -INFINITY;
+      if (k_base + i + 1 >= last_valid) v1 = -INFINITY;
+      if (k_base + i + 2 >= last_valid) v2 = -INFINITY;
+      if (k_base + i + 3 >= last_valid) v3 = -INFINITY;
+    }
+    bm[0] = fmaxf(bm[0], v0); bm[1] = fmaxf(bm[1], v1); bm[2] = fmaxf(bm[2], v2); bm[3] = fmaxf(bm[3], v3);
+    const float p0 = ex2_approx(fmaf(v0, scale_log2, mneg));
+    const float p1 = ex2_approx(fmaf(v1, scale_log2, mneg));
+    const float p2 = ex2_approx(fmaf(v2, scale_log2, mneg));
+    const float p3 = ex2_approx(fmaf(v3, scale_log2, mneg));
+    ps[0] += p0; ps[1] += p1; ps[2] += p2; ps[3] += p3;
+    pk[i >> 1] = pack_bf16x2(p0, p1);
+    pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+  }
+  tmem_st_32x16(t_p_chunk, pk);
+}
+
+// exp2 pass over one key block of one query row: P = exp2(s*c - m_ref*c) -> bf16 -> TMEM, row max
+// tracked on the side.  TAIL = last block of the utterance (keys beyond its end masked).
+template <bool TAIL>
+__device__ __forceinline__ void exp_pass(uint32_t t_s, uint32_t t_p, int n_chunks, int last_valid,
+                                         float scale_log2, float m_ref, float& bm_out, float& psum_out) {
+  const float mneg = -m_ref * scale_log2;
+  float ps[4] = {0.f, 0.f, 0.f, 0.f};
+  float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    if (TAIL && c >= n_chunks) break;
+    uint32_t s[32];
+    tmem_ld_32x32p(t_s + c * 32, s);
+    tmem_ld_wait();
+    exp_chunk<TAIL>(s, t_p + c * 16, c * 32, last_valid, scale_log2, mneg, bm, ps);
+  }
+  bm_out = fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3]));
+  psum_out = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+}
+
+// Row max of one key block (first block only: later blocks exponentiate speculatively).
+template <bool TAIL>
+__device__ __forceinline__ float max_pass(uint32_t t_s, int n_chunks, int last_valid) {
   float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
 #pragma unroll 1
   for (int g = 0; g < 2; ++g) {
@@ -91,7 +135,7 @@ __device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_o, uint64
       for (int i = 0; i < 64; i += 4) {
         float v0 = __uint_as_float(s[i]), v1 = __uint_as_float(s[i + 1]);
         float v2 = __uint_as_float(s[i + 2]), v3 = __uint_as_float(s[i + 3]);
-        if (TAIL) {                                        // key beyond the utterance
+        if (TAIL) {
           if (g * 64 + i >= last_valid) v0 = -INFINITY;
           if (g * 64 + i + 1 >= last_valid) v1 = -INFINITY;
           if (g * 64 + i + 2 >= last_valid) v2 = -INFINITY;
@@ -101,12 +145,29 @@ __device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_o, uint64
       }
     }
   }
-  const float bm = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
-  // lazy reference max: rescale O / l only when the max grew by more than 2^8
-  const bool need = (bm - m_ref) * scale_log2 > RESCALE_LOG2;   // also true on the first block
+  return fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
+}
+
+// One key block of one query tile, executed by the 128 threads that own the tile's rows.
+// Block 0 takes the exact row max first.  Later blocks exponentiate against the reference max
+// m_ref carried over from earlier blocks in a single TMEM pass and only fall back (rescale O and
+// l, redo the pass) when some row's max grew by more than 2^8 — exact, because the common factor
+// 2^(m_ref c) cancels in O / l, and bounded: p <= 2^8 in every committed pass.
+template <bool TAIL>
+__device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_p, uint32_t t_o, uint64_t* pv_done_x,
+                                              int j, int n_chunks, int last_valid, float scale_log2,
+                                              float& m_ref, float& l) {
+  using namespace attn;
+  float bm, psum;
   if (j == 0) {
-    m_ref = bm;
-  } else if (__any_sync(0xffffffffu, need)) {
+    m_ref = max_pass<TAIL>(t_s, n_chunks, last_valid);
+    exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum);
+    l = psum;
+    return;
+  }
+  exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum);
+  const bool need = (bm - m_ref) * scale_log2 > RESCALE_LOG2;
+  if (__any_sync(0xffffffffu, need)) {
     mbar_wait(pv_done_x, (j - 1) & 1);                    // O_x quiescent: PV_x(j-1) retired
     tc_fence_after();
     const float alpha = need ? ex2_approx((m_ref - bm) * scale_log2) : 1.0f;
@@ -120,45 +181,9 @@ __device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_o, uint64
       for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
       tmem_st_32x32p(t_o + c * 32, o);
     }
-    tmem_st_wait();
+    exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum);   // S_x(j) is still intact
   }
-  // pass 2: P = exp2(s*c - m_ref*c) -> bf16 -> TMEM, over the S columns already consumed
-  const float mneg = -m_ref * scale_log2;
-  float ps0 = 0.f, ps1 = 0.f, ps2 = 0.f, ps3 = 0.f;
-#pragma unroll 1
-  for (int g = 0; g < 2; ++g) {
-    if (!TAIL || 2 * g < n_chunks) {
-      uint32_t s[64];
-      tmem_ld_32x32p(t_s + g * 64, s);
-      if (!TAIL || 2 * g + 1 < n_chunks) tmem_ld_32x32p(t_s + g * 64 + 32, s + 32);
-      tmem_ld_wait();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        if (!TAIL || 2 * g + c < n_chunks) {
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i]), scale_log2, mneg));
-            float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 1]), scale_log2, mneg));
-            float p2 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 2]), scale_log2, mneg));
-            float p3 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 3]), scale_log2, mneg));
-            if (TAIL) {
-              const int k0 = g * 64 + c * 32 + i;
-              if (k0 >= last_valid) p0 = 0.f;
-              if (k0 + 1 >= last_valid) p1 = 0.f;
-              if (k0 + 2 >= last_valid) p2 = 0.f;
-              if (k0 + 3 >= last_valid) p3 = 0.f;
-            }
-            ps0 += p0; ps1 += p1; ps2 += p2; ps3 += p3;
-            pk[i >> 1] = pack_bf16x2(p0, p1);
-            pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-          }
-          tmem_st_32x16(t_s + (2 * g + c) * 16, pk);
-        }
-      }
-    }
-  }
-  l += (ps0 + ps1) + (ps2 + ps3);
+  l += psum;
 }
 
 __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
@@ -243,7 +268,7 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
         const int s = j % KV_STAGES;
         const int ksteps = ((j == nblk - 1) ? last_n : BKV) / 16;
         const uint32_t sv = smem_u32(s_kv + s * 2 * TILE_BYTES + TILE_BYTES);
-        const uint32_t t_p = tmem_base + COL_S + x * 128;       // P aliases the S columns
+        const uint32_t t_p = tmem_base + COL_P + x * 64;
         const uint32_t t_o = tmem_base + COL_O + x * 64;
         for (int k = 0; k < ksteps; ++k) {
           const uint64_t dv = umma_desc_mnmajor_sw128(sv + k * 16 * 128, 1024);
@@ -259,11 +284,11 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
         const bool more = j + 1 < nblk;
         if (more) mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
         for (int x = 0; x < n_tiles; ++x) {
-          mbar_wait(&p_full[x], j & 1);                  // P_x(j) in TMEM, O_x rescaled if needed
+          mbar_wait(&p_full[x], j & 1);                  // P_x(j) in TMEM, S_x consumed, O_x rescaled if needed
           tc_fence_after();
+          if (more) issue_s(x, j + 1);                   // next scores first: the softmax warps wait on these
           issue_pv(x, j);
           if (x == n_tiles - 1) umma_commit(&kv_empty[j % KV_STAGES]);   // K_j / V_j consumed by both tiles
-          if (more) issue_s(x, j + 1);                   // overwrites S_x/P_x(j): ordered after PV_x(j)
         }
       }
     }
@@ -275,6 +300,7 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
       const int r_tile = quad * 32 + lane;             // query row inside the tile
       const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
       const uint32_t t_s = tmem_base + lane_off + COL_S + x * 128;
+      const uint32_t t_p = tmem_base + lane_off + COL_P + x * 64;
       const uint32_t t_o = tmem_base + lane_off + COL_O + x * 64;
       float m_ref = -INFINITY, l = 0.f;
 
@@ -282,8 +308,8 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
         const bool tail = (j == nblk - 1) && last_valid < BKV;
         mbar_wait(&s_full[x], j & 1);
         tc_fence_after();
-        if (!tail) softmax_block<false>(t_s, t_o, &pv_done[x], j, 4, BKV, scale_log2, m_ref, l);
-        else softmax_block<true>(t_s, t_o, &pv_done[x], j, (last_n + 31) / 32, last_valid, scale_log2, m_ref, l);
+        if (!tail) softmax_block<false>(t_s, t_p, t_o, &pv_done[x], j, 4, BKV, scale_log2, m_ref, l);
+        else softmax_block<true>(t_s, t_p, t_o, &pv_done[x], j, (last_n + 31) / 32, last_valid, scale_log2, m_ref, l);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[x]);

@@ -145,6 +145,77 @@ __global__ void __launch_bounds__(256) norm_kernel(
   }
 }
 
+// AdaLN for d = NV*256 with the [gamma | beta] row of the current timestep cached in registers:
+// each warp walks a CONTIGUOUS range of rows (same utterance => same table row), so the table is
+// re-read only at utterance boundaries and the steady state moves 4d bytes in, 2d bytes out.
+template <int NV>
+__global__ void __launch_bounds__(256) adaln_rows_kernel(
+    __nv_bfloat16* __restrict__ out, const float* __restrict__ x, const float* __restrict__ table,
+    const int32_t* __restrict__ level_utt, const int32_t* __restrict__ row_utt, int M, int rows_per_warp,
+    float eps, float k, float c) {
+  constexpr int d = NV * 256;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int r_begin = warp_global * rows_per_warp;
+  const int r_end = min(r_begin + rows_per_warp, M);
+  float g[NV][8], bt[NV][8];
+  int cached = -1;
+  for (int r = r_begin; r < r_end; ++r) {
+    const float* xr = x + static_cast<size_t>(r) * d;
+    float v[NV][8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(xr + i * 256 + lane * 8));
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(xr + i * 256 + lane * 8 + 4));
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+      v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+    }
+    const int lvl = level_utt[row_utt[r]];
+    if (lvl != cached) {                               // warp-uniform
+      const float* gp = table + static_cast<size_t>(lvl) * 2 * d;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp + i * 256 + lane * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + i * 256 + lane * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(gp + d + i * 256 + lane * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(gp + d + i * 256 + lane * 8 + 4));
+        g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w;
+        g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+        bt[i][0] = b0.x; bt[i][1] = b0.y; bt[i][2] = b0.z; bt[i][3] = b0.w;
+        bt[i][4] = b1.x; bt[i][5] = b1.y; bt[i][6] = b1.z; bt[i][7] = b1.w;
+      }
+      cached = lvl;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+    const float mean = warp_sum(s) * (1.0f / d);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const float dv = v[i][e] - mean; q += dv * dv; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / d) + eps);
+    __nv_bfloat16* orow = out + static_cast<size_t>(r) * d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float h = (v[i][e] - mean) * rstd;
+        h = c * (1.f - k * h) * h;
+        y[e] = fmaf(g[i][e], h, bt[i][e]);
+      }
+      uint4 o;
+      o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+      o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+      *reinterpret_cast<uint4*>(orow + i * 256 + lane * 8) = o;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(
     __nv_bfloat16* __restrict__ out, const float* __restrict__ x,
     const int32_t* __restrict__ row_index, int n_rows, int d) {
@@ -202,8 +273,24 @@ extern "C" int vb200_adaln(void* out_bf16, const float* x, const float* table,
   VB_REQUIRE(out_bf16 && x && table && level_utt && row_utt, "adaln: null pointer");
   VB_REQUIRE(d > 0 && d % 8 == 0 && d <= 2048, "adaln: d=%d must be a multiple of 8, <= 2048", d);
   if (M <= 0) return VB200_OK;
-  norm_kernel<0><<<row_grid(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(out_bf16), x, table, nullptr, level_utt, row_utt, M, d, eps, k, c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
+  if (d % 256 == 0 && d <= 1024) {
+    // contiguous row ranges per warp; enough warps for ~4 resident blocks per SM
+    const int total_warps = num_sms() * 4 * 8;
+    int rpw = (M + total_warps - 1) / total_warps;
+    if (rpw < 4) rpw = 4;
+    const int warps = (M + rpw - 1) / rpw;
+    const int grid = (warps + 7) / 8;
+    switch (d / 256) {
+      case 1: adaln_rows_kernel<1><<<grid, 256, 0, st>>>(o, x, table, level_utt, row_utt, M, rpw, eps, k, c); break;
+      case 2: adaln_rows_kernel<2><<<grid, 256, 0, st>>>(o, x, table, level_utt, row_utt, M, rpw, eps, k, c); break;
+      case 3: adaln_rows_kernel<3><<<grid, 256, 0, st>>>(o, x, table, level_utt, row_utt, M, rpw, eps, k, c); break;
+      default: adaln_rows_kernel<4><<<grid, 256, 0, st>>>(o, x, table, level_utt, row_utt, M, rpw, eps, k, c); break;
+    }
+  } else {
+    norm_kernel<0><<<row_grid(M, 8), 256, 0, st>>>(o, x, table, nullptr, level_utt, row_utt, M, d, eps, k, c);
+  }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
