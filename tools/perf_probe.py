@@ -75,17 +75,20 @@ def small_kernels():
 
 
 if __name__ == "__main__":
-    small_kernels()
-    for B in (1, 32):
-        M = 1027 * B
-        gemm(M, 3072, 1024, L.EPI_NONE, torch.bfloat16)
-        gemm(M, 1024, 1024, L.EPI_BIAS_RESIDUAL, torch.float32)
-        gemm(M, 4096, 1024, L.EPI_BIAS_GELU, torch.bfloat16)
-        gemm(M, 1024, 4096, L.EPI_BIAS_RESIDUAL, torch.float32)
-    gemm(750 * 32, 8192, 1024, L.EPI_BIAS, torch.float16)
-    for v in ("tmem",):
-        try:
-            attn([1027] * 32, 16, v)
-            attn([2527] * 8, 16, v)
-        except Exception as e:  # bring-up: keep going
-            print("attn", v, "failed:", e)
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "small"):
+        small_kernels()
+    if what in ("all", "gemm"):
+        for B in (1, 32):
+            M = 1027 * B
+            gemm(M, 3072, 1024, L.EPI_NONE, torch.bfloat16)
+            gemm(M, 1024, 1024, L.EPI_BIAS_RESIDUAL, torch.float32)
+            gemm(M, 4096, 1024, L.EPI_BIAS_GELU, torch.bfloat16)
+            gemm(M, 1024, 4096, L.EPI_BIAS_RESIDUAL, torch.float32)
+        gemm(750 * 32, 8192, 1024, L.EPI_BIAS, torch.float16)
+    if what in ("all", "attn"):
+        import os
+        print("VB200_ATTN_VARIANT", os.environ.get("VB200_ATTN_VARIANT"))
+        attn([1027] * 32, 16, "tmem")
+        attn([2527] * 8, 16, "tmem")
+        attn([1027] * 256, 16, "tmem")

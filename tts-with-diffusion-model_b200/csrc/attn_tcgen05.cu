@@ -18,6 +18,8 @@
 // Keys past the utterance end are masked to -inf — the reference's key-padding mask
 // (base.py:119-124) in the packed-row layout — and the last key block only issues the MMAs
 // (N resp. K rounded up to 16) its valid keys need.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vb200 {
@@ -76,7 +78,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 template <bool TAIL>
 __device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint32_t t_p_chunk, int k_base,
                                           int last_valid, float scale_log2, float mneg,
-                                          float (&bm)[4], float (&ps)[4]) {
+                                          float (&bm)[4], float (&ps)[4], uint64_t* wait_bar,
+                                          uint32_t wait_parity) {
   uint32_t pk[16];
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
@@ -97,6 +100,10 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint32_t t_p_
     pk[i >> 1] = pack_bf16x2(p0, p1);
     pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
   }
+  if (wait_bar) {             // P_x(j-1) is still being read by PV_x(j-1) until this barrier flips
+    mbar_wait(wait_bar, wait_parity);
+    tc_fence_after();
+  }
   tmem_st_32x16(t_p_chunk, pk);
 }
 
@@ -104,7 +111,8 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint32_t t_p_
 // tracked on the side.  TAIL = last block of the utterance (keys beyond its end masked).
 template <bool TAIL>
 __device__ __forceinline__ void exp_pass(uint32_t t_s, uint32_t t_p, int n_chunks, int last_valid,
-                                         float scale_log2, float m_ref, float& bm_out, float& psum_out) {
+                                         float scale_log2, float m_ref, float& bm_out, float& psum_out,
+                                         uint64_t* wait_bar, uint32_t wait_parity) {
   const float mneg = -m_ref * scale_log2;
   float ps[4] = {0.f, 0.f, 0.f, 0.f};
   float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -114,7 +122,8 @@ __device__ __forceinline__ void exp_pass(uint32_t t_s, uint32_t t_p, int n_chunk
     uint32_t s[32];
     tmem_ld_32x32p(t_s + c * 32, s);
     tmem_ld_wait();
-    exp_chunk<TAIL>(s, t_p + c * 16, c * 32, last_valid, scale_log2, mneg, bm, ps);
+    exp_chunk<TAIL>(s, t_p + c * 16, c * 32, last_valid, scale_log2, mneg, bm, ps, c == 0 ? wait_bar : nullptr,
+                    wait_parity);
   }
   bm_out = fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3]));
   psum_out = (ps[0] + ps[1]) + (ps[2] + ps[3]);
@@ -153,7 +162,7 @@ __device__ __forceinline__ float max_pass(uint32_t t_s, int n_chunks, int last_v
 // m_ref carried over from earlier blocks in a single TMEM pass and only fall back (rescale O and
 // l, redo the pass) when some row's max grew by more than 2^8 — exact, because the common factor
 // 2^(m_ref c) cancels in O / l, and bounded: p <= 2^8 in every committed pass.
-template <bool TAIL>
+template <bool TAIL, bool SPEC>
 __device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_p, uint32_t t_o, uint64_t* pv_done_x,
                                               int j, int n_chunks, int last_valid, float scale_log2,
                                               float& m_ref, float& l) {
@@ -161,14 +170,20 @@ __device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_p, uint32
   float bm, psum;
   if (j == 0) {
     m_ref = max_pass<TAIL>(t_s, n_chunks, last_valid);
-    exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum);
+    exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum, nullptr, 0);
     l = psum;
     return;
   }
-  exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum);
+  const uint32_t prev = (j - 1) & 1;
+  if (SPEC) {
+    exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum, pv_done_x, prev);
+  } else {
+    bm = max_pass<TAIL>(t_s, n_chunks, last_valid);
+  }
   const bool need = (bm - m_ref) * scale_log2 > RESCALE_LOG2;
-  if (__any_sync(0xffffffffu, need)) {
-    mbar_wait(pv_done_x, (j - 1) & 1);                    // O_x quiescent: PV_x(j-1) retired
+  const bool any_need = __any_sync(0xffffffffu, need);
+  if (any_need) {
+    mbar_wait(pv_done_x, prev);                           // O_x quiescent: PV_x(j-1) retired
     tc_fence_after();
     const float alpha = need ? ex2_approx((m_ref - bm) * scale_log2) : 1.0f;
     if (need) { m_ref = bm; l *= alpha; }
@@ -181,11 +196,13 @@ __device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_p, uint32
       for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
       tmem_st_32x32p(t_o + c * 32, o);
     }
-    exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum);   // S_x(j) is still intact
   }
+  if (!SPEC || any_need)                                  // S_x(j) is still intact in TMEM
+    exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum, pv_done_x, prev);
   l += psum;
 }
 
+template <bool SPEC, bool S_FIRST>
 __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
     const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
     const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
@@ -286,8 +303,9 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
         for (int x = 0; x < n_tiles; ++x) {
           mbar_wait(&p_full[x], j & 1);                  // P_x(j) in TMEM, S_x consumed, O_x rescaled if needed
           tc_fence_after();
-          if (more) issue_s(x, j + 1);                   // next scores first: the softmax warps wait on these
+          if (S_FIRST && more) issue_s(x, j + 1);        // next scores first: the softmax warps wait on these
           issue_pv(x, j);
+          if (!S_FIRST && more) issue_s(x, j + 1);
           if (x == n_tiles - 1) umma_commit(&kv_empty[j % KV_STAGES]);   // K_j / V_j consumed by both tiles
         }
       }
@@ -308,8 +326,8 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
         const bool tail = (j == nblk - 1) && last_valid < BKV;
         mbar_wait(&s_full[x], j & 1);
         tc_fence_after();
-        if (!tail) softmax_block<false>(t_s, t_p, t_o, &pv_done[x], j, 4, BKV, scale_log2, m_ref, l);
-        else softmax_block<true>(t_s, t_p, t_o, &pv_done[x], j, (last_n + 31) / 32, last_valid, scale_log2, m_ref, l);
+        if (!tail) softmax_block<false, SPEC>(t_s, t_p, t_o, &pv_done[x], j, 4, BKV, scale_log2, m_ref, l);
+        else softmax_block<true, SPEC>(t_s, t_p, t_o, &pv_done[x], j, (last_n + 31) / 32, last_valid, scale_log2, m_ref, l);
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[x]);
@@ -366,14 +384,33 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
   int rc = cached_tmap(&tm, VB200_BF16, qkv_bf16, static_cast<uint64_t>(3) * d, M,
                        static_cast<uint64_t>(3) * d * 2, HD, 128);
   if (rc != VB200_OK) return rc;
-  static bool configured = false;
-  if (!configured) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
+  // bring-up knob: VB200_ATTN_VARIANT = bit0 speculative single-pass softmax, bit1 S-first issue order
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("VB200_ATTN_VARIANT");
+    variant = e ? atoi(e) & 3 : 3;
   }
   dim3 grid((max_T + 2 * BQ - 1) / (2 * BQ), n_heads, B);
-  flash_attn_kernel<<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-      tm, static_cast<__nv_bfloat16*>(out_bf16), cu_rows, n_heads, scale * 1.4426950408889634f);
+  const float sl2 = scale * 1.4426950408889634f;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
+#define VB_ATTN_LAUNCH(SP, SF)                                                                          \
+  do {                                                                                                  \
+    static bool configured = false;                                                                     \
+    if (!configured) {                                                                                  \
+      VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<SP, SF>,                                     \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));     \
+      configured = true;                                                                                \
+    }                                                                                                   \
+    flash_attn_kernel<SP, SF><<<grid, THREADS, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);         \
+  } while (0)
+  switch (variant) {
+    case 0: VB_ATTN_LAUNCH(false, false); break;
+    case 1: VB_ATTN_LAUNCH(true, false); break;
+    case 2: VB_ATTN_LAUNCH(false, true); break;
+    default: VB_ATTN_LAUNCH(true, true); break;
+  }
+#undef VB_ATTN_LAUNCH
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

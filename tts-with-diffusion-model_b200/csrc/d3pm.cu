@@ -280,6 +280,44 @@ __global__ void __launch_bounds__(256) posterior_sample_kernel(
 }
 
 
+// 8 logits as one 16-byte word (2-byte types) or two (fp32), and their unpacking to fp32.
+template <typename T> struct Raw8 { uint4 a; };
+template <> struct Raw8<float> { uint4 a, b; };
+template <typename T>
+__device__ __forceinline__ Raw8<T> load_raw8(const T* p) {
+  Raw8<T> r;
+  r.a = __ldcs(reinterpret_cast<const uint4*>(p));
+  return r;
+}
+template <>
+__device__ __forceinline__ Raw8<float> load_raw8<float>(const float* p) {
+  Raw8<float> r;
+  r.a = __ldcs(reinterpret_cast<const uint4*>(p));
+  r.b = __ldcs(reinterpret_cast<const uint4*>(p) + 1);
+  return r;
+}
+__device__ __forceinline__ void unpack8(const Raw8<__half>& r, float* v) {
+  const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    v[2 * i] = f.x;
+    v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float* v) {
+  const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float* v) {
+  v[0] = __uint_as_float(r.a.x); v[1] = __uint_as_float(r.a.y); v[2] = __uint_as_float(r.a.z); v[3] = __uint_as_float(r.a.w);
+  v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
+}
+
 // ---------------------------------------------------------------- P, production form
 // Register-resident O(K) reverse step for K = 256*KC (<= 1024): one warp per token, the K logits
 // are read from HBM exactly once (16-byte loads), softmax statistics stay in registers, and the
@@ -294,7 +332,7 @@ __global__ void __launch_bounds__(256) posterior_sample_kernel(
 // is closed form; the per-class weights are only walked when the draw lands in the generic part.
 // Greedy mode (argmax of the same weights) needs no logarithm either.
 template <typename T, int KC, int NOISE>
-__global__ void __launch_bounds__(256) posterior_fast_kernel(
+__global__ void __launch_bounds__(256, 3) posterior_fast_kernel(
     int32_t* __restrict__ x_out, const T* __restrict__ logits, int64_t ld_logits,
     const int32_t* __restrict__ x_t_all, const int32_t* __restrict__ row_utt,
     const int32_t* __restrict__ t_utt, const int32_t* __restrict__ utt,
@@ -306,21 +344,35 @@ __global__ void __launch_bounds__(256) posterior_fast_kernel(
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tok = n_rows * n_levels;
-  for (int tok = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tok < n_tok;
-       tok += gridDim.x * warps_per_block) {
+  const int stride = gridDim.x * warps_per_block;
+  int tok = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  // software pipeline over this warp's tokens: the next token's logits (still packed) and its two
+  // special-class logits are in flight while the current token is reduced
+  Raw8<T> nxt[KC];
+  float nxt_lx = 0.f, nxt_lm = 0.f;
+  int nxt_xt = 0;
+  const int m_abs = K / 2;
+  auto prefetch = [&](int tk) {
+    const int rw = tk / n_levels, lv = tk - rw * n_levels;
+    const T* lr = logits + static_cast<size_t>(rw) * ld_logits + static_cast<size_t>(lv) * K;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) nxt[c] = load_raw8<T>(lr + c * 256 + lane * 8);
+    nxt_xt = x_t_all[tk];
+    nxt_lx = load_logit<T>(lr, nxt_xt);
+    nxt_lm = load_logit<T>(lr, m_abs);
+  };
+  if (tok < n_tok) prefetch(tok);
+  for (; tok < n_tok; tok += stride) {
     const int row = tok / n_levels, level = tok - row * n_levels;
     const int b = row_utt[row];
     const int t = min(max(t_utt[b], 0), S - 1);
-    const T* lrow = logits + static_cast<size_t>(row) * ld_logits + static_cast<size_t>(level) * K;
     // lane owns classes j = c*256 + lane*8 + i  (c < KC, i < 8) in registers v[c*8 + i]
     float v[NR];
 #pragma unroll
-    for (int c = 0; c < KC; ++c) {
-      float tmp[8];
-      load8<T>(lrow + c * 256 + lane * 8, tmp);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[c * 8 + i] = tmp[i];
-    }
+    for (int c = 0; c < KC; ++c) unpack8(nxt[c], v + c * 8);
+    const int x_t = nxt_xt;
+    const float l_x = nxt_lx, l_m = nxt_lm;
+    if (tok + stride < n_tok) prefetch(tok + stride);
     // argmax of the logits (lowest index wins ties) and row max
     Best top{-INFINITY, 0x7fffffff};
 #pragma unroll
@@ -361,7 +413,6 @@ __global__ void __launch_bounds__(256) posterior_fast_kernel(
     const int t1 = t - 1;
     const float* one = table + static_cast<size_t>(t) * VB200_TAB_STRIDE;
     const float* cum = table + static_cast<size_t>(t1) * VB200_TAB_STRIDE;
-    const int x_t = x_t_all[tok];
     const bool absorbing = transition == VB200_ABSORBING;
     const int m = absorbing ? K / 2 : -1;
     const bool at_m = x_t == m;
@@ -373,13 +424,13 @@ __global__ void __launch_bounds__(256) posterior_fast_kernel(
     const float coef = (a_gen - c_gen) * invZ * f1_oth;
     const float cst = (c_gen + kEps) * f1_oth;
     // special classes: true weight minus what the generic formula assigns them (>= 0)
-    const float e_x = exp2f_fast((load_logit<T>(lrow, x_t) - mx) * kLog2e);
+    const float e_x = exp2f_fast((l_x - mx) * kLog2e);
     const float ax = at_m ? a_m : a_gen, cx = at_m ? c_m : c_gen;
     const float w_x = f1_self * (fmaf(e_x * invZ, ax - cx, cx) + kEps);
     const float dx = fmaxf(w_x - fmaf(e_x, coef, cst), 0.f);
     float w_m = 0.f, dm = 0.f;
     if (absorbing && !at_m) {
-      const float e_m = exp2f_fast((load_logit<T>(lrow, m) - mx) * kLog2e);
+      const float e_m = exp2f_fast((l_m - mx) * kLog2e);
       w_m = f1_oth * (fmaf(e_m * invZ, a_m - c_m, c_m) + kEps);
       dm = fmaxf(w_m - fmaf(e_m, coef, cst), 0.f);
     }
