@@ -310,6 +310,29 @@ def run_ours(args, wl):
                               "frac": attn_tf / peak_tf, "avg_launch_ms": at[1] / at[2],
                               "share_of_denoise_step": (at[1] / prof_steps) / step_total_ms}}
 
+    # ---------------- p50 denoise-step latency (BASELINE.json's second metric): C2 shape, batch 1,
+    # one CUDA-graph replay = denoiser forward + posterior + sample, >= 20 warm iterations
+    latency = None
+    if rank == 0:
+        b1, tt1, tp1, tr1, _, _ = WORKLOADS["c2"]
+        text1, proms1 = synth_batch(1, tt1, tp1, seed=7)
+        ses1 = model._session([t.to(dev) for t in text1], [p.to(dev) for p in proms1], [tr1], [0])
+        ses1.x_t.fill_(model.mask_id)
+        ses1.run(table, timesteps, tr, noise=L.NOISE_PHILOX, seed=args.seed, use_graph=True)   # captures the step graph
+        lat = []
+        for _ in range(40):
+            ses1.t_utt.fill_(timesteps // 2)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ses1.graph.replay()
+            b.record()
+            torch.cuda.synchronize(dev)
+            lat.append(a.elapsed_time(b))
+        lat = sorted(lat[10:])
+        latency = {"p50_denoise_step_ms": lat[len(lat) // 2], "p90_denoise_step_ms": lat[int(len(lat) * 0.9)],
+                   "workload": f"c2: batch 1, T={tt1 + tp1 + tr1 + 2} rows ({tr1} frames x 8 levels), one graph replay per step",
+                   "tokens_per_sec_batch1": tr1 * 8 / (lat[len(lat) // 2] * 1e-3 * (timesteps - 1))}
+
     # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample of the oracle port
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -333,7 +356,7 @@ def run_ours(args, wl):
                 "clocks": clocks.summary(),
                 "e2e": {"value": tokens_per_step / (e2e / 1e3), "unit": UNIT, "ms_per_step": e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu_baseline}
+                "gpu_launches": launches, "roofline": roofline, "latency": latency, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -27,10 +27,9 @@ namespace vb200 {
 namespace attn {
 constexpr int BQ = 128, BKV = 128, HD = 64, KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: 128 rows x 128 B
-constexpr int THREADS = 10 * 32;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;   // S_X at 128*X, P_X at 256+64*X, O_X at 384+64*X
-constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
+constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256 + 2 * 512 * 4;
 constexpr float RESCALE_LOG2 = 8.0f;
 }  // namespace attn
 
@@ -202,8 +201,81 @@ __device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_p, uint32
   l += psum;
 }
 
-template <bool SPEC, bool S_FIRST>
-__global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
+
+// SPLIT == 2: the 128 scores of a row are shared by two threads (same TMEM lane, different warps
+// with the same warp % 4), 64 columns each, which doubles the warps available to hide MUFU and
+// TMEM latency.  The two exchange their partial row maxima through shared memory and a 64-thread
+// named barrier, so both use the same reference max; row sums are combined once, in the epilogue.
+template <bool TAIL>
+__device__ __forceinline__ void softmax_block_split(uint32_t t_s, uint32_t t_p, uint32_t t_o, uint64_t* pv_done_x,
+                                                    int j, int n_chunks, int last_valid, float scale_log2,
+                                                    int hh, int r_tile, float* xm, int bar_id,
+                                                    float& m_ref, float& l) {
+  using namespace attn;
+  // pass 1: partial row max over this thread's 64 columns
+  float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    const int cc = hh * 2 + c;
+    if (TAIL && cc >= n_chunks) break;
+    uint32_t s[32];
+    tmem_ld_32x32p(t_s + cc * 32, s);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      float v0 = __uint_as_float(s[i]), v1 = __uint_as_float(s[i + 1]);
+      float v2 = __uint_as_float(s[i + 2]), v3 = __uint_as_float(s[i + 3]);
+      if (TAIL) {
+        const int k0 = cc * 32 + i;
+        if (k0 >= last_valid) v0 = -INFINITY;
+        if (k0 + 1 >= last_valid) v1 = -INFINITY;
+        if (k0 + 2 >= last_valid) v2 = -INFINITY;
+        if (k0 + 3 >= last_valid) v3 = -INFINITY;
+      }
+      bm0 = fmaxf(bm0, v0); bm1 = fmaxf(bm1, v1); bm2 = fmaxf(bm2, v2); bm3 = fmaxf(bm3, v3);
+    }
+  }
+  float bm = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
+  xm[hh * 128 + r_tile] = bm;
+  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+  bm = fmaxf(bm, xm[(hh ^ 1) * 128 + r_tile]);
+  const uint32_t prev = (j - 1) & 1;
+  if (j == 0) {
+    m_ref = bm;
+  } else {
+    const bool need = (bm - m_ref) * scale_log2 > RESCALE_LOG2;   // same value in both threads of the row
+    if (__any_sync(0xffffffffu, need)) {
+      mbar_wait(pv_done_x, prev);                         // O_x quiescent: PV_x(j-1) retired
+      tc_fence_after();
+      const float alpha = need ? ex2_approx((m_ref - bm) * scale_log2) : 1.0f;
+      if (need) { m_ref = bm; l *= alpha; }
+      uint32_t o[32];                                     // this thread rescales 32 of the 64 O columns
+      tmem_ld_32x32p(t_o + hh * 32, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st_32x32p(t_o + hh * 32, o);
+    }
+  }
+  // pass 2
+  const float mneg = -m_ref * scale_log2;
+  float ps[4] = {0.f, 0.f, 0.f, 0.f};
+  float dummy[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    const int cc = hh * 2 + c;
+    if (TAIL && cc >= n_chunks) break;
+    uint32_t s[32];
+    tmem_ld_32x32p(t_s + cc * 32, s);
+    tmem_ld_wait();
+    exp_chunk<TAIL>(s, t_p + cc * 16, cc * 32, last_valid, scale_log2, mneg, dummy, ps,
+                    (j > 0 && c == 0) ? pv_done_x : nullptr, prev);
+  }
+  l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+}
+
+template <bool SPEC, bool S_FIRST, int SPLIT>
+__global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
     const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
     const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
   using namespace attn;
@@ -230,6 +302,7 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
   uint64_t* p_full = s_full + 2;                  // [2]  P_X(j) written (128 arrivals)
   uint64_t* pv_done = p_full + 2;                 // [2]  O_X += P_X(j) V_j retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  float* xch = reinterpret_cast<float*>(bars + 32);   // SPLIT == 2: [tile][parity][half][128] row maxima / sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -237,7 +310,7 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
     tma_prefetch_desc(&tm_qkv);
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128); mbar_init(&pv_done[x], 1); }
+    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 128 * SPLIT); mbar_init(&pv_done[x], 1); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -312,7 +385,9 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
     }
   } else {
     // ------------------------------------------------------------ softmax / output warps
-    const int x = (warp - 2) >> 2;                     // 0: tile A, 1: tile B
+    const int e = warp - 2;
+    const int x = e / (4 * SPLIT);                     // 0: tile A, 1: tile B
+    const int hh = (e >> 2) % SPLIT;                   // which column share of the row (SPLIT == 2)
     if (x == 0 || has_b) {
       const int quad = warp & 3;
       const int r_tile = quad * 32 + lane;             // query row inside the tile
@@ -321,13 +396,21 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
       const uint32_t t_p = tmem_base + lane_off + COL_P + x * 64;
       const uint32_t t_o = tmem_base + lane_off + COL_O + x * 64;
       float m_ref = -INFINITY, l = 0.f;
+      float* xch_t = xch + x * 512;                    // [parity][half][128]
+      const int bar_id = 1 + x * 4 + quad;             // named barrier of the two warps sharing these rows
 
       for (int j = 0; j < nblk; ++j) {
         const bool tail = (j == nblk - 1) && last_valid < BKV;
         mbar_wait(&s_full[x], j & 1);
         tc_fence_after();
-        if (!tail) softmax_block<false, SPEC>(t_s, t_p, t_o, &pv_done[x], j, 4, BKV, scale_log2, m_ref, l);
-        else softmax_block<true, SPEC>(t_s, t_p, t_o, &pv_done[x], j, (last_n + 31) / 32, last_valid, scale_log2, m_ref, l);
+        if (SPLIT == 1) {
+          if (!tail) softmax_block<false, SPEC>(t_s, t_p, t_o, &pv_done[x], j, 4, BKV, scale_log2, m_ref, l);
+          else softmax_block<true, SPEC>(t_s, t_p, t_o, &pv_done[x], j, (last_n + 31) / 32, last_valid, scale_log2, m_ref, l);
+        } else {
+          float* xm = xch_t + (j & 1) * 256;
+          if (!tail) softmax_block_split<false>(t_s, t_p, t_o, &pv_done[x], j, 4, BKV, scale_log2, hh, r_tile, xm, bar_id, m_ref, l);
+          else softmax_block_split<true>(t_s, t_p, t_o, &pv_done[x], j, (last_n + 31) / 32, last_valid, scale_log2, hh, r_tile, xm, bar_id, m_ref, l);
+        }
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_full[x]);
@@ -336,22 +419,29 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
       mbar_wait(&pv_done[x], (nblk - 1) & 1);
       tc_fence_after();
       const int q_row = (qp * 2 + x) * BQ + r_tile;
-      const float inv = 1.0f / l;
       __nv_bfloat16* o_dst = out + static_cast<size_t>(row0 + q_row) * d + h * HD;
+      if (SPLIT == 2) {                                // total row sum = both column shares
+        float* xl = xch_t + (nblk & 1) * 256;
+        xl[hh * 128 + r_tile] = l;
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        l += xl[(hh ^ 1) * 128 + r_tile];
+      }
+      const float inv = 1.0f / l;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
+        if (SPLIT == 2 && c != hh) continue;           // each of the two warps stores 32 of the 64 columns
         uint32_t o[32];
         tmem_ld_32x32p(t_o + c * 32, o);
         tmem_ld_wait();
         if (q_row < T) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
-            uint4 p;
-            p.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
-            p.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
-            p.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
-            p.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
-            *reinterpret_cast<uint4*>(o_dst + c * 32 + i) = p;
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(o[i]) * inv, __uint_as_float(o[i + 1]) * inv);
+            pk.y = pack_bf16x2(__uint_as_float(o[i + 2]) * inv, __uint_as_float(o[i + 3]) * inv);
+            pk.z = pack_bf16x2(__uint_as_float(o[i + 4]) * inv, __uint_as_float(o[i + 5]) * inv);
+            pk.w = pack_bf16x2(__uint_as_float(o[i + 6]) * inv, __uint_as_float(o[i + 7]) * inv);
+            *reinterpret_cast<uint4*>(o_dst + c * 32 + i) = pk;
           }
         }
       }
@@ -384,31 +474,34 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
   int rc = cached_tmap(&tm, VB200_BF16, qkv_bf16, static_cast<uint64_t>(3) * d, M,
                        static_cast<uint64_t>(3) * d * 2, HD, 128);
   if (rc != VB200_OK) return rc;
-  // bring-up knob: VB200_ATTN_VARIANT = bit0 speculative single-pass softmax, bit1 S-first issue order
+  // bring-up knob: VB200_ATTN_VARIANT = bit0 speculative single-pass softmax (SPLIT 1 only), bit1 S-first
+  // issue order, bit2 two warps per row quadrant (SPLIT 2)
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("VB200_ATTN_VARIANT");
-    variant = e ? atoi(e) & 3 : 3;
+    variant = e ? atoi(e) & 7 : 6;
   }
   dim3 grid((max_T + 2 * BQ - 1) / (2 * BQ), n_heads, B);
   const float sl2 = scale * 1.4426950408889634f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
-#define VB_ATTN_LAUNCH(SP, SF)                                                                          \
+#define VB_ATTN_LAUNCH(SP, SF, SL)                                                                      \
   do {                                                                                                  \
     static bool configured = false;                                                                     \
     if (!configured) {                                                                                  \
-      VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<SP, SF>,                                     \
+      VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<SP, SF, SL>,                                 \
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));     \
       configured = true;                                                                                \
     }                                                                                                   \
-    flash_attn_kernel<SP, SF><<<grid, THREADS, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);         \
+    flash_attn_kernel<SP, SF, SL><<<grid, (2 + 8 * SL) * 32, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2); \
   } while (0)
   switch (variant) {
-    case 0: VB_ATTN_LAUNCH(false, false); break;
-    case 1: VB_ATTN_LAUNCH(true, false); break;
-    case 2: VB_ATTN_LAUNCH(false, true); break;
-    default: VB_ATTN_LAUNCH(true, true); break;
+    case 0: VB_ATTN_LAUNCH(false, false, 1); break;
+    case 1: VB_ATTN_LAUNCH(true, false, 1); break;
+    case 2: VB_ATTN_LAUNCH(false, true, 1); break;
+    case 3: VB_ATTN_LAUNCH(true, true, 1); break;
+    case 4: case 5: VB_ATTN_LAUNCH(false, false, 2); break;
+    default: VB_ATTN_LAUNCH(false, true, 2); break;
   }
 #undef VB_ATTN_LAUNCH
   VB_CHECK_CUDA(cudaGetLastError());
