@@ -273,3 +273,58 @@ def test_philox_sampling_matches_posterior_distribution(L):
     L.posterior_sample_from_logits(out2, None, logits, K, x_t, row_utt, t_utt, utt, table, n, 1, K, L.ABSORBING,
                                    L.NOISE_PHILOX, seed=77)
     assert torch.equal(out, out2)           # counter-based: reproducible
+
+
+@pytest.mark.parametrize("transition", ["absorbing", "uniform"])
+@pytest.mark.parametrize("K", [256, 1024])
+def test_fast_posterior_kernel_matches_generic(L, transition, K):
+    """The register-resident production kernel (K % 256 == 0) against the generic log-domain kernel:
+    identical greedy codes, and inverse-CDF draws distributed as the posterior (chi-square)."""
+    from vall_e.vall_e import d3pm as pd
+    S = 40
+    code = L.ABSORBING if transition == "absorbing" else L.UNIFORM
+    table = pd.scalar_table(S, K, transition).to(DEV)
+    g = torch.Generator().manual_seed(K)
+    # (a) greedy equality on varied rows / timesteps / x_t (masked and unmasked)
+    rows, levels = 300, 2
+    logits = (torch.randn(rows, levels * K, generator=g) * 3).half().to(DEV)
+    x_t = torch.randint(0, K, (rows, levels), generator=g, dtype=torch.int32)
+    x_t[::3] = K // 2
+    x_t = x_t.to(DEV)
+    B = 6
+    row_utt = (torch.arange(rows, dtype=torch.int32) % B).sort().values.to(DEV)
+    t_utt = torch.tensor([0, 1, 5, 20, 38, 39], dtype=torch.int32, device=DEV)
+    utt = torch.zeros(B, L.U_STRIDE, dtype=torch.int32, device=DEV)
+    fast = torch.empty(rows, levels, dtype=torch.int32, device=DEV)
+    slow = torch.empty_like(fast)
+    post = torch.empty(rows * levels, K, dtype=torch.float32, device=DEV)
+    args = (levels * K, x_t, row_utt, t_utt, utt, table, rows, levels, K, code)
+    L.posterior_sample_from_logits(fast, None, logits, *args, L.NOISE_GREEDY)
+    L.posterior_sample_from_logits(slow, post, logits, *args, L.NOISE_GREEDY)
+    top2 = post.topk(2, dim=-1).values
+    clear = ((top2[:, 0] - top2[:, 1]) > 1e-3).view(rows, levels)
+    assert clear.float().mean().item() > 0.9
+    assert torch.equal(fast[clear], slow[clear])
+    # (b) distribution of the inverse-CDF sampler, masked and unmasked current token
+    n = 30000
+    row = (torch.randn(K, generator=g) * 2.0).half()
+    lg = row.repeat(n, 1).to(DEV)
+    for xt_val in (K // 2, 3):
+        xt = torch.full((n, 1), xt_val, dtype=torch.int32, device=DEV)
+        ru = torch.zeros(n, dtype=torch.int32, device=DEV)
+        tu = torch.tensor([17], dtype=torch.int32, device=DEV)
+        u1 = torch.zeros(1, L.U_STRIDE, dtype=torch.int32, device=DEV)
+        out = torch.empty(n, 1, dtype=torch.int32, device=DEV)
+        pp = torch.empty(n, K, dtype=torch.float32, device=DEV)
+        L.posterior_sample_from_logits(out, None, lg, K, xt, ru, tu, u1, table, n, 1, K, code, L.NOISE_PHILOX, seed=5)
+        L.posterior_sample_from_logits(torch.empty_like(out), pp, lg, K, xt, ru, tu, u1, table, n, 1, K, code, L.NOISE_GREEDY)
+        p = torch.softmax(pp[0].double().cpu(), -1)
+        counts = torch.bincount(out.view(-1).cpu().long(), minlength=K).double()
+        expected = p * n
+        keep = expected > 5
+        chi2 = (((counts - expected) ** 2) / expected)[keep].sum().item()
+        rest_obs, rest_exp = counts[~keep].sum().item(), expected[~keep].sum().item()
+        if rest_exp > 5:
+            chi2 += (rest_obs - rest_exp) ** 2 / rest_exp
+        dof = max(int(keep.sum().item()), 2)
+        assert chi2 < dof + 6 * math.sqrt(2 * dof), (transition, K, xt_val, chi2, dof)

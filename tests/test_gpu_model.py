@@ -188,3 +188,48 @@ def test_cpu_tensors_fail_loudly():
     m = NAR(64, d_model=64, n_heads=1, n_layers=1)
     with pytest.raises(L.VB200Error):
         m([torch.tensor([1, 2])], [torch.zeros(3, 8, dtype=torch.long)], [torch.zeros(4, 1, dtype=torch.long)])
+
+
+def test_layernorm_variant_and_nar_level_loop():
+    """norm_type == 'ln' (base.py:175-176) through the same kernels, and the NAR level loop API."""
+    from oracle import denoiser as on
+    from vall_e.vall_e.base import Base
+    from vall_e.vall_e.nar import NAR
+
+    class LnModel(Base):
+        casual = False
+        n_resp_levels = 7
+        use_stop_token = False
+        norm_type = "ln"
+        resp_loss_only = True
+
+    K, d, h, nl = 64, 128, 2, 2
+    torch.manual_seed(0)
+    m = LnModel(K, d_model=d, n_heads=h, n_layers=nl)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(p.bfloat16().float())
+        for blk in m.blocks:
+            for sub in (blk.attn, blk.ffn):
+                sub.norm.weight.copy_((1 + 0.1 * torch.randn(d)).bfloat16().float())
+                sub.norm.bias.copy_((0.1 * torch.randn(d)).bfloat16().float())
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    m = m.to(DEV)
+    lens = [(5, 9, 40), (8, 17, 140)]
+    g = torch.Generator().manual_seed(4)
+    text = [torch.randint(1, K, (a,), generator=g) for a, _, _ in lens]
+    proms = [torch.randint(0, K, (b, 8), generator=g) for _, b, _ in lens]
+    resps = [torch.randint(0, K, (c, 2), generator=g) for _, _, c in lens]
+    ref = on.base_forward_logits(sd, text, proms, resps, torch.zeros(2, dtype=torch.long), h, nl, norm_type="ln")
+    got = m._logits([x.to(DEV) for x in text], [x.to(DEV) for x in proms], [x.to(DEV) for x in resps],
+                    torch.zeros(2, dtype=torch.long), use_time=False)
+    for r, g_, rs in zip(ref, got, resps):
+        assert (g_.cpu() - r[-len(rs):]).abs().max().item() <= 2e-2
+
+    nar = NAR(K, d_model=d, n_heads=h, n_layers=nl).to(DEV)
+    out = nar([x.to(DEV) for x in text], [x.to(DEV) for x in proms], [r[:, :1].to(DEV) for r in resps])
+    assert [tuple(o.shape) for o in out] == [(40, 8), (140, 8)]
+    assert all(torch.equal(o[:, 0].cpu(), r[:, 0]) for o, r in zip(out, resps))
+    assert all(int(o.min()) >= 0 and int(o.max()) < K for o in out)
+    with pytest.raises(ValueError):
+        nar([x.to(DEV) for x in text], [x.to(DEV) for x in proms], [resps[0][:, :1].to(DEV), resps[1][:, :2].to(DEV)])

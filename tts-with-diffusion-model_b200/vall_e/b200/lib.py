@@ -6,12 +6,13 @@ passed as raw device pointers; every call runs on torch's current CUDA stream.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libvalle_b200.so"
+LIB_PATH = Path(os.environ.get("VB200_LIB", _HERE / "libvalle_b200.so"))   # override: bring-up experiments only
 
 OK = 0
 F32, BF16, F16 = 0, 1, 2
