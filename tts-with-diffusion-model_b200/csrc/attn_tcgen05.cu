@@ -2,22 +2,27 @@
 // base.py:112-127 materialises (b, i, j, h) scores + mask + softmax in HBM).
 //
 // One CTA = (utterance, head, PAIR of 128-query tiles A/B); it walks the utterance's keys in
-// blocks of 128 and keeps the tensor pipe busy by ping-ponging the two tiles:
+// blocks of 128.  12 warps:
 //   warp 0 lane 0 : TMA producer  — Q_A, Q_B once, then K/V blocks through a 3-stage ring
 //   warp 1 lane 0 : MMA issuer    — S_X = Q_X K^T   (tcgen05.mma 128xNx16, SS, both K-major)
 //                                   O_X += P_X V    (128x64x16, A = P_X from TMEM, B = V straight
 //                                                    from the TMA tile as an MN-major operand)
-//   warps 2..5    : softmax of tile A, warps 6..9: softmax of tile B — thread = one query row:
-//                   one tcgen05.ld pass of the 128 scores per block: exp2 against a reference max
-//                   carried over from earlier blocks (exact max pass only for block 0), P (bf16)
-//                   written to its own TMEM columns, so S_X(j+1) can be issued before P_X(j) V_j.
-// O accumulates in TMEM across key blocks (fp32); it is rescaled only when the running max
-// grows by more than 2^8 (exact: the common factor cancels in O / l), so the steady state has no
-// TMEM round trip for O.  While tile A's threads do exponentials the tensor pipe runs tile B's
-// MMAs and vice versa.  TMEM (512 columns): S_A 128 | S_B 128 | P_A 64 | P_B 64 | O_A 64 | O_B 64.
+//   warps 4..7    : softmax of tile A, warps 8..11: softmax of tile B — thread = one query row.
+// Measured on B200: the softmax -> MMA -> softmax round trip (mbarrier hops + MMA latency) costs
+// ~900 cycles per hop pair, more than the MMAs themselves, so the dependency chain has to be
+// taken off the critical path ("early release", MODE 1): a softmax thread pulls all 128 scores of
+// its row into registers with ONE pass of tcgen05.ld and immediately signals s_free; the MMA warp
+// issues S_X(j+1) right then, i.e. a whole softmax block (~1000 cycles) ahead of its use.  The
+// 128 live scores need ~190 registers, so the control warpgroup gives its registers away
+// (setmaxnreg.dec 88) and the two softmax warpgroups grow to 200 (setmaxnreg.inc).
+// P (bf16) goes to its own TMEM columns and feeds O_X += P_X V; O accumulates in TMEM across key
+// blocks (fp32) and is rescaled only when the row max grows by more than 2^8 (exact: the common
+// factor cancels in O / l).  TMEM (512 columns): S_A 128 | S_B 128 | P_A 64 | P_B 64 | O_A 64 | O_B 64.
 // Keys past the utterance end are masked to -inf — the reference's key-padding mask
 // (base.py:119-124) in the packed-row layout — and the last key block only issues the MMAs
 // (N resp. K rounded up to 16) its valid keys need.
+// MODE 0 keeps the first validated schedule (two tcgen05.ld passes, S_X(j+1) issued when P_X(j) is
+// written) for A/B measurements: VB200_ATTN_VARIANT=0.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -29,11 +34,12 @@ constexpr int BQ = 128, BKV = 128, HD = 64, KV_STAGES = 3;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: 128 rows x 128 B
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;   // S_X at 128*X, P_X at 256+64*X, O_X at 384+64*X
-constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256 + 2 * 512 * 4;
+constexpr int THREADS = 12 * 32;          // control warpgroup + two softmax warpgroups
+constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
 constexpr float RESCALE_LOG2 = 8.0f;
 }  // namespace attn
 
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r) {
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
       "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -42,7 +48,7 @@ __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* r)
       "r"(r[14]), "r"(r[15])
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld_32x32p(uint32_t taddr, uint32_t* r) {
+__device__ __forceinline__ void tmem_ld_32x32p(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
@@ -55,7 +61,7 @@ __device__ __forceinline__ void tmem_ld_32x32p(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x32p(uint32_t taddr, const uint32_t* r) {
+__device__ __forceinline__ void tmem_st_32x32p(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
       "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
@@ -67,38 +73,34 @@ __device__ __forceinline__ void tmem_st_32x32p(uint32_t taddr, const uint32_t* r
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
-#ifdef VB200_ATTN_NOEXP   // timing experiment only: replaces the exponential by an FMA-pipe op
-__device__ __forceinline__ float ex2_approx(float x) { return fmaf(x, 0.001f, 1.0f); }
-#else
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-#endif
 
-// 32 scores of one row -> 32 probabilities (bf16, 16 TMEM columns); max / sum tracked on 4 chains.
-template <bool TAIL>
-__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint32_t t_p_chunk, int k_base,
-                                          int last_valid, float scale_log2, float mneg,
-                                          float (&bm)[4], float (&ps)[4], uint64_t* wait_bar,
-                                          uint32_t wait_parity) {
+
+// 32 scores -> 32 probabilities (bf16, 16 TMEM columns); row sum tracked on 4 chains.
+__device__ __forceinline__ void exp_store_chunk(const uint32_t (&s)[32], uint32_t t_p_chunk, float scale_log2,
+                                                float mneg, float (&ps)[4], uint64_t* wait_bar,
+                                                uint32_t wait_parity) {
   uint32_t pk[16];
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
-    float v0 = __uint_as_float(s[i]), v1 = __uint_as_float(s[i + 1]);
-    float v2 = __uint_as_float(s[i + 2]), v3 = __uint_as_float(s[i + 3]);
-    if (TAIL) {                                    // key beyond the utterance: exp2(-inf) = 0
-      if (k_base + i >= last_valid) v0 = -INFINITY;
-      if (k_base + i + 1 >= last_valid) v1 = -INFINITY;
-      if (k_base + i + 2 >= last_valid) v2 = -INFINITY;
-      if (k_base + i + 3 >= last_valid) v3 = -INFINITY;
-    }
-    bm[0] = fmaxf(bm[0], v0); bm[1] = fmaxf(bm[1], v1); bm[2] = fmaxf(bm[2], v2); bm[3] = fmaxf(bm[3], v3);
-    const float p0 = ex2_approx(fmaf(v0, scale_log2, mneg));
-    const float p1 = ex2_approx(fmaf(v1, scale_log2, mneg));
-    const float p2 = ex2_approx(fmaf(v2, scale_log2, mneg));
-    const float p3 = ex2_approx(fmaf(v3, scale_log2, mneg));
+    const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, mneg));
+    const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg));
+    const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), scale_log2, mneg));
+    const float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), scale_log2, mneg));
     ps[0] += p0; ps[1] += p1; ps[2] += p2; ps[3] += p3;
     pk[i >> 1] = pack_bf16x2(p0, p1);
     pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
@@ -110,14 +112,88 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint32_t t_p_
   tmem_st_32x16(t_p_chunk, pk);
 }
 
-// exp2 pass over one key block of one query row: P = exp2(s*c - m_ref*c) -> bf16 -> TMEM, row max
-// tracked on the side.  TAIL = last block of the utterance (keys beyond its end masked).
+// max of 32 scores on 4 chains; TAIL masks keys beyond the utterance (and writes the mask back)
 template <bool TAIL>
-__device__ __forceinline__ void exp_pass(uint32_t t_s, uint32_t t_p, int n_chunks, int last_valid,
-                                         float scale_log2, float m_ref, float& bm_out, float& psum_out,
-                                         uint64_t* wait_bar, uint32_t wait_parity) {
-  const float mneg = -m_ref * scale_log2;
+__device__ __forceinline__ void max_chunk(uint32_t (&s)[32], int k_base, int last_valid, float (&bm)[4]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    float v0 = __uint_as_float(s[i]), v1 = __uint_as_float(s[i + 1]);
+    float v2 = __uint_as_float(s[i + 2]), v3 = __uint_as_float(s[i + 3]);
+    if (TAIL) {
+      if (k_base + i >= last_valid) v0 = -INFINITY;
+      if (k_base + i + 1 >= last_valid) v1 = -INFINITY;
+      if (k_base + i + 2 >= last_valid) v2 = -INFINITY;
+      if (k_base + i + 3 >= last_valid) v3 = -INFINITY;
+      s[i] = __float_as_uint(v0); s[i + 1] = __float_as_uint(v1);
+      s[i + 2] = __float_as_uint(v2); s[i + 3] = __float_as_uint(v3);
+    }
+    bm[0] = fmaxf(bm[0], v0); bm[1] = fmaxf(bm[1], v1); bm[2] = fmaxf(bm[2], v2); bm[3] = fmaxf(bm[3], v3);
+  }
+}
+
+// Lazy reference max: rescale O_x / l only when the block max exceeds m_ref by more than 2^8.
+__device__ __forceinline__ void update_reference(float bm, int j, float scale_log2, uint32_t t_o,
+                                                 uint64_t* pv_done_x, float& m_ref, float& l) {
+  using namespace attn;
+  if (j == 0) { m_ref = bm; return; }
+  const bool need = (bm - m_ref) * scale_log2 > RESCALE_LOG2;
+  if (__any_sync(0xffffffffu, need)) {
+    mbar_wait(pv_done_x, (j - 1) & 1);                    // O_x quiescent: PV_x(j-1) retired
+    tc_fence_after();
+    const float alpha = need ? ex2_approx((m_ref - bm) * scale_log2) : 1.0f;
+    if (need) { m_ref = bm; l *= alpha; }
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {                         // 16 columns at a time: this path is rare and
+      uint32_t o[16];                                     // must not add to the register peak
+      tmem_ld_32x16(t_o + c * 16, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+      tmem_st_32x16(t_o + c * 16, o);
+    }
+  }
+}
+
+// MODE 1: one key block of one query row, scores held in registers, S_x released before the math.
+template <bool TAIL>
+__device__ __forceinline__ void softmax_block_early(uint32_t t_s, uint32_t t_p, uint32_t t_o, uint64_t* pv_done_x,
+                                                    uint64_t* s_free_x, int j, int n_chunks, int last_valid,
+                                                    float scale_log2, int lane, float& m_ref, float& l) {
+  uint32_t s0[32], s1[32], s2[32], s3[32];       // four named arrays: keeps all 128 scores in registers
+  const bool a1 = !TAIL || n_chunks > 1, a2 = !TAIL || n_chunks > 2, a3 = !TAIL || n_chunks > 3;
+  tmem_ld_32x32p(t_s, s0);
+  if (a1) tmem_ld_32x32p(t_s + 32, s1);
+  if (a2) tmem_ld_32x32p(t_s + 64, s2);
+  if (a3) tmem_ld_32x32p(t_s + 96, s3);
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(s_free_x);                   // S_x(j) is in registers: S_x(j+1) may be issued
+  float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  max_chunk<TAIL>(s0, 0, last_valid, bm);
+  if (a1) max_chunk<TAIL>(s1, 32, last_valid, bm);
+  if (a2) max_chunk<TAIL>(s2, 64, last_valid, bm);
+  if (a3) max_chunk<TAIL>(s3, 96, last_valid, bm);
+  update_reference(fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3])), j, scale_log2, t_o, pv_done_x, m_ref, l);
+  float mneg = -m_ref * scale_log2;
   float ps[4] = {0.f, 0.f, 0.f, 0.f};
+  // the empty asm statements order the four chunks for the scheduler: without them all 128
+  // exponentials are hoisted ahead of the packing and the live range doubles
+  exp_store_chunk(s0, t_p, scale_log2, mneg, ps, j > 0 ? pv_done_x : nullptr, (j - 1) & 1);
+  asm volatile("" : "+f"(mneg));
+  if (a1) exp_store_chunk(s1, t_p + 16, scale_log2, mneg, ps, nullptr, 0);
+  asm volatile("" : "+f"(mneg));
+  if (a2) exp_store_chunk(s2, t_p + 32, scale_log2, mneg, ps, nullptr, 0);
+  asm volatile("" : "+f"(mneg));
+  if (a3) exp_store_chunk(s3, t_p + 48, scale_log2, mneg, ps, nullptr, 0);
+  l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+}
+
+// MODE 0: two passes over S_x in TMEM (max, then exp), 32 columns at a time.
+template <bool TAIL>
+__device__ __forceinline__ void softmax_block_classic(uint32_t t_s, uint32_t t_p, uint32_t t_o, uint64_t* pv_done_x,
+                                                      int j, int n_chunks, int last_valid, float scale_log2,
+                                                      float& m_ref, float& l) {
   float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
@@ -125,161 +201,26 @@ __device__ __forceinline__ void exp_pass(uint32_t t_s, uint32_t t_p, int n_chunk
     uint32_t s[32];
     tmem_ld_32x32p(t_s + c * 32, s);
     tmem_ld_wait();
-    exp_chunk<TAIL>(s, t_p + c * 16, c * 32, last_valid, scale_log2, mneg, bm, ps, c == 0 ? wait_bar : nullptr,
-                    wait_parity);
+    max_chunk<TAIL>(s, c * 32, last_valid, bm);
   }
-  bm_out = fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3]));
-  psum_out = (ps[0] + ps[1]) + (ps[2] + ps[3]);
-}
-
-// Row max of one key block (first block only: later blocks exponentiate speculatively).
-template <bool TAIL>
-__device__ __forceinline__ float max_pass(uint32_t t_s, int n_chunks, int last_valid) {
-  float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
-#pragma unroll 1
-  for (int g = 0; g < 2; ++g) {
-    if (!TAIL || 2 * g < n_chunks) {
-      uint32_t s[64];
-      tmem_ld_32x32p(t_s + g * 64, s);
-      if (!TAIL || 2 * g + 1 < n_chunks) tmem_ld_32x32p(t_s + g * 64 + 32, s + 32);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 64; i += 4) {
-        float v0 = __uint_as_float(s[i]), v1 = __uint_as_float(s[i + 1]);
-        float v2 = __uint_as_float(s[i + 2]), v3 = __uint_as_float(s[i + 3]);
-        if (TAIL) {
-          if (g * 64 + i >= last_valid) v0 = -INFINITY;
-          if (g * 64 + i + 1 >= last_valid) v1 = -INFINITY;
-          if (g * 64 + i + 2 >= last_valid) v2 = -INFINITY;
-          if (g * 64 + i + 3 >= last_valid) v3 = -INFINITY;
-        }
-        bm0 = fmaxf(bm0, v0); bm1 = fmaxf(bm1, v1); bm2 = fmaxf(bm2, v2); bm3 = fmaxf(bm3, v3);
-      }
-    }
-  }
-  return fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
-}
-
-// One key block of one query tile, executed by the 128 threads that own the tile's rows.
-// Block 0 takes the exact row max first.  Later blocks exponentiate against the reference max
-// m_ref carried over from earlier blocks in a single TMEM pass and only fall back (rescale O and
-// l, redo the pass) when some row's max grew by more than 2^8 — exact, because the common factor
-// 2^(m_ref c) cancels in O / l, and bounded: p <= 2^8 in every committed pass.
-template <bool TAIL, bool SPEC>
-__device__ __forceinline__ void softmax_block(uint32_t t_s, uint32_t t_p, uint32_t t_o, uint64_t* pv_done_x,
-                                              int j, int n_chunks, int last_valid, float scale_log2,
-                                              float& m_ref, float& l) {
-  using namespace attn;
-  float bm, psum;
-  if (j == 0) {
-    m_ref = max_pass<TAIL>(t_s, n_chunks, last_valid);
-    exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum, nullptr, 0);
-    l = psum;
-    return;
-  }
-  const uint32_t prev = (j - 1) & 1;
-  if (SPEC) {
-    exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum, pv_done_x, prev);
-  } else {
-    bm = max_pass<TAIL>(t_s, n_chunks, last_valid);
-  }
-  const bool need = (bm - m_ref) * scale_log2 > RESCALE_LOG2;
-  const bool any_need = __any_sync(0xffffffffu, need);
-  if (any_need) {
-    mbar_wait(pv_done_x, prev);                           // O_x quiescent: PV_x(j-1) retired
-    tc_fence_after();
-    const float alpha = need ? ex2_approx((m_ref - bm) * scale_log2) : 1.0f;
-    if (need) { m_ref = bm; l *= alpha; }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tmem_ld_32x32p(t_o + c * 32, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-      tmem_st_32x32p(t_o + c * 32, o);
-    }
-  }
-  if (!SPEC || any_need)                                  // S_x(j) is still intact in TMEM
-    exp_pass<TAIL>(t_s, t_p, n_chunks, last_valid, scale_log2, m_ref, bm, psum, pv_done_x, prev);
-  l += psum;
-}
-
-
-// SPLIT == 2: the 128 scores of a row are shared by two threads (same TMEM lane, different warps
-// with the same warp % 4), 64 columns each, which doubles the warps available to hide MUFU and
-// TMEM latency.  The two exchange their partial row maxima through shared memory and a 64-thread
-// named barrier, so both use the same reference max; row sums are combined once, in the epilogue.
-template <bool TAIL>
-__device__ __forceinline__ void softmax_block_split(uint32_t t_s, uint32_t t_p, uint32_t t_o, uint64_t* pv_done_x,
-                                                    int j, int n_chunks, int last_valid, float scale_log2,
-                                                    int hh, int r_tile, float* xm, int bar_id,
-                                                    float& m_ref, float& l) {
-  using namespace attn;
-  // pass 1: partial row max over this thread's 64 columns
-  float bm0 = -INFINITY, bm1 = -INFINITY, bm2 = -INFINITY, bm3 = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    const int cc = hh * 2 + c;
-    if (TAIL && cc >= n_chunks) break;
-    uint32_t s[32];
-    tmem_ld_32x32p(t_s + cc * 32, s);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      float v0 = __uint_as_float(s[i]), v1 = __uint_as_float(s[i + 1]);
-      float v2 = __uint_as_float(s[i + 2]), v3 = __uint_as_float(s[i + 3]);
-      if (TAIL) {
-        const int k0 = cc * 32 + i;
-        if (k0 >= last_valid) v0 = -INFINITY;
-        if (k0 + 1 >= last_valid) v1 = -INFINITY;
-        if (k0 + 2 >= last_valid) v2 = -INFINITY;
-        if (k0 + 3 >= last_valid) v3 = -INFINITY;
-      }
-      bm0 = fmaxf(bm0, v0); bm1 = fmaxf(bm1, v1); bm2 = fmaxf(bm2, v2); bm3 = fmaxf(bm3, v3);
-    }
-  }
-  float bm = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
-  xm[hh * 128 + r_tile] = bm;
-  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-  bm = fmaxf(bm, xm[(hh ^ 1) * 128 + r_tile]);
-  const uint32_t prev = (j - 1) & 1;
-  if (j == 0) {
-    m_ref = bm;
-  } else {
-    const bool need = (bm - m_ref) * scale_log2 > RESCALE_LOG2;   // same value in both threads of the row
-    if (__any_sync(0xffffffffu, need)) {
-      mbar_wait(pv_done_x, prev);                         // O_x quiescent: PV_x(j-1) retired
-      tc_fence_after();
-      const float alpha = need ? ex2_approx((m_ref - bm) * scale_log2) : 1.0f;
-      if (need) { m_ref = bm; l *= alpha; }
-      uint32_t o[32];                                     // this thread rescales 32 of the 64 O columns
-      tmem_ld_32x32p(t_o + hh * 32, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-      tmem_st_32x32p(t_o + hh * 32, o);
-    }
-  }
-  // pass 2
+  update_reference(fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3])), j, scale_log2, t_o, pv_done_x, m_ref, l);
   const float mneg = -m_ref * scale_log2;
   float ps[4] = {0.f, 0.f, 0.f, 0.f};
-  float dummy[4] = {0.f, 0.f, 0.f, 0.f};
+  float unused[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
-  for (int c = 0; c < 2; ++c) {
-    const int cc = hh * 2 + c;
-    if (TAIL && cc >= n_chunks) break;
+  for (int c = 0; c < 4; ++c) {
+    if (TAIL && c >= n_chunks) break;
     uint32_t s[32];
-    tmem_ld_32x32p(t_s + cc * 32, s);
+    tmem_ld_32x32p(t_s + c * 32, s);
     tmem_ld_wait();
-    exp_chunk<TAIL>(s, t_p + cc * 16, cc * 32, last_valid, scale_log2, mneg, dummy, ps,
-                    (j > 0 && c == 0) ? pv_done_x : nullptr, prev);
+    if (TAIL) max_chunk<true>(s, c * 32, last_valid, unused);     // re-apply the key mask
+    exp_store_chunk(s, t_p + c * 16, scale_log2, mneg, ps, (c == 0 && j > 0) ? pv_done_x : nullptr, (j - 1) & 1);
   }
   l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
 }
 
-template <bool SPEC, bool S_FIRST, int SPLIT>
-__global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
+template <int MODE>
+__global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
     const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
     const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
   using namespace attn;
@@ -305,8 +246,8 @@ __global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
   uint64_t* s_full = kv_empty + KV_STAGES;        // [2]  S_X(j) complete
   uint64_t* p_full = s_full + 2;                  // [2]  P_X(j) written (one arrival per softmax warp)
   uint64_t* pv_done = p_full + 2;                 // [2]  O_X += P_X(j) V_j retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
-  float* xch = reinterpret_cast<float*>(bars + 32);   // SPLIT == 2: [tile][parity][half][128] row maxima / sums
+  uint64_t* s_free = pv_done + 2;                 // [2]  MODE 1: S_X(j) pulled into registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -314,7 +255,9 @@ __global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
     tma_prefetch_desc(&tm_qkv);
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int x = 0; x < 2; ++x) { mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 4 * SPLIT); mbar_init(&pv_done[x], 1); }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 4); mbar_init(&pv_done[x], 1); mbar_init(&s_free[x], 4);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -326,8 +269,10 @@ __global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (warp < 4) {
+    // ============================================================== control warpgroup
+    if (MODE == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (warp == 0 && lane == 0) {
       // ---------------------------------------------------------- TMA producer
       mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
       tma_load_2d(s_q, &tm_qkv, q_full, h * HD, row0 + qp * 2 * BQ);
@@ -341,13 +286,11 @@ __global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
         tma_load_2d(sk, &tm_qkv, &kv_full[s], d + h * HD, row0 + j * BKV);
         tma_load_2d(sk + TILE_BYTES, &tm_qkv, &kv_full[s], 2 * d + h * HD, row0 + j * BKV);
       }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
+    } else if (warp == 1 && lane == 0) {
       // ---------------------------------------------------------- MMA issuer
       // One thread feeds the tensor pipe; everything it needs per MMA is a 32-bit add on a
       // precomputed descriptor (smem addresses are < 2^18, so the 14-bit start-address field of
-      // the low word never carries): the loop body must stay short, the softmax warps wait on it.
+      // the low word never carries).
       const uint32_t idesc_o = umma_idesc_bf16(BQ, HD, false, true);        // B = V, MN-major
       const uint32_t idesc_s_full = umma_idesc_bf16(BQ, BKV, false, false);
       const uint32_t idesc_s_last = umma_idesc_bf16(BQ, last_n, false, false);
@@ -369,7 +312,6 @@ __global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
         const uint64_t dv = dv_base + static_cast<uint32_t>(j % KV_STAGES) * (2 * kTileStep);
         const uint32_t t_p = tmem_base + COL_P + x * 64;
         const uint32_t t_o = tmem_base + COL_O + x * 64;
-#if !defined(VB200_ATTN_NOPV)
         if (j != nblk - 1) {
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k)                   // 16 key rows = 16 * 128 B = 128 units
@@ -378,7 +320,6 @@ __global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
           const int ksteps = last_n / 16;
           for (int k = 0; k < ksteps; ++k) umma_ts(t_o, t_p + k * 8, dv + k * 128, idesc_o, (j | k) != 0);
         }
-#endif
         umma_commit(&pv_done[x]);
       };
       mbar_wait(q_full, 0);
@@ -388,21 +329,34 @@ __global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
       for (int j = 0; j < nblk; ++j) {
         const bool more = j + 1 < nblk;
         if (more) mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
-        for (int x = 0; x < n_tiles; ++x) {
-          mbar_wait(&p_full[x], j & 1);                  // P_x(j) in TMEM, S_x consumed, O_x rescaled if needed
-          tc_fence_after();
-          if (S_FIRST && more) issue_s(x, j + 1);        // next scores first: the softmax warps wait on these
-          issue_pv(x, j);
-          if (!S_FIRST && more) issue_s(x, j + 1);
-          if (x == n_tiles - 1) umma_commit(&kv_empty[j % KV_STAGES]);   // K_j / V_j consumed by both tiles
+        if (MODE == 1) {
+          // early release: S_x(j+1) as soon as S_x(j) sits in the softmax registers, P_x(j) V_j later
+          if (more)
+            for (int x = 0; x < n_tiles; ++x) {
+              mbar_wait(&s_free[x], j & 1);
+              tc_fence_after();
+              issue_s(x, j + 1);
+            }
+          for (int x = 0; x < n_tiles; ++x) {
+            mbar_wait(&p_full[x], j & 1);
+            tc_fence_after();
+            issue_pv(x, j);
+          }
+        } else {
+          for (int x = 0; x < n_tiles; ++x) {
+            mbar_wait(&p_full[x], j & 1);                // P_x(j) in TMEM, S_x consumed, O_x rescaled if needed
+            tc_fence_after();
+            if (more) issue_s(x, j + 1);                 // next scores first: the softmax warps wait on these
+            issue_pv(x, j);
+          }
         }
+        umma_commit(&kv_empty[j % KV_STAGES]);           // K_j / V_j consumed by both tiles
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax / output warps
-    const int e = warp - 2;
-    const int x = e / (4 * SPLIT);                     // 0: tile A, 1: tile B
-    const int hh = (e >> 2) % SPLIT;                   // which column share of the row (SPLIT == 2)
+    // ============================================================== softmax / output warpgroups
+    if (MODE == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+    const int x = (warp - 4) >> 2;                     // 0: tile A, 1: tile B
     if (x == 0 || has_b) {
       const int quad = warp & 3;
       const int r_tile = quad * 32 + lane;             // query row inside the tile
@@ -411,26 +365,18 @@ __global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
       const uint32_t t_p = tmem_base + lane_off + COL_P + x * 64;
       const uint32_t t_o = tmem_base + lane_off + COL_O + x * 64;
       float m_ref = -INFINITY, l = 0.f;
-      float* xch_t = xch + x * 512;                    // [parity][half][128]
-      const int bar_id = 1 + x * 4 + quad;             // named barrier of the two warps sharing these rows
 
       for (int j = 0; j < nblk; ++j) {
         const bool tail = (j == nblk - 1) && last_valid < BKV;
+        const int n_chunks = tail ? (last_n + 31) / 32 : 4;
         mbar_wait(&s_full[x], j & 1);
         tc_fence_after();
-#if defined(VB200_ATTN_NOSOFTMAX)
-        if (false) {
-#else
-        if (SPLIT == 1) {
-#endif
-          if (!tail) softmax_block<false, SPEC>(t_s, t_p, t_o, &pv_done[x], j, 4, BKV, scale_log2, m_ref, l);
-          else softmax_block<true, SPEC>(t_s, t_p, t_o, &pv_done[x], j, (last_n + 31) / 32, last_valid, scale_log2, m_ref, l);
-        } else if (SPLIT == 2) {
-#if !defined(VB200_ATTN_NOSOFTMAX)
-          float* xm = xch_t + (j & 1) * 256;
-          if (!tail) softmax_block_split<false>(t_s, t_p, t_o, &pv_done[x], j, 4, BKV, scale_log2, hh, r_tile, xm, bar_id, m_ref, l);
-          else softmax_block_split<true>(t_s, t_p, t_o, &pv_done[x], j, (last_n + 31) / 32, last_valid, scale_log2, hh, r_tile, xm, bar_id, m_ref, l);
-#endif
+        if (MODE == 1) {
+          if (!tail) softmax_block_early<false>(t_s, t_p, t_o, &pv_done[x], &s_free[x], j, 4, BKV, scale_log2, lane, m_ref, l);
+          else softmax_block_early<true>(t_s, t_p, t_o, &pv_done[x], &s_free[x], j, n_chunks, last_valid, scale_log2, lane, m_ref, l);
+        } else {
+          if (!tail) softmax_block_classic<false>(t_s, t_p, t_o, &pv_done[x], j, 4, BKV, scale_log2, m_ref, l);
+          else softmax_block_classic<true>(t_s, t_p, t_o, &pv_done[x], j, n_chunks, last_valid, scale_log2, m_ref, l);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -441,17 +387,10 @@ __global__ void __launch_bounds__((2 + 8 * SPLIT) * 32, 1) flash_attn_kernel(
       mbar_wait(&pv_done[x], (nblk - 1) & 1);
       tc_fence_after();
       const int q_row = (qp * 2 + x) * BQ + r_tile;
-      __nv_bfloat16* o_dst = out + static_cast<size_t>(row0 + q_row) * d + h * HD;
-      if (SPLIT == 2) {                                // total row sum = both column shares
-        float* xl = xch_t + (nblk & 1) * 256;
-        xl[hh * 128 + r_tile] = l;
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-        l += xl[(hh ^ 1) * 128 + r_tile];
-      }
       const float inv = 1.0f / l;
+      __nv_bfloat16* o_dst = out + static_cast<size_t>(row0 + q_row) * d + h * HD;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        if (SPLIT == 2 && c != hh) continue;           // each of the two warps stores 32 of the 64 columns
         uint32_t o[32];
         tmem_ld_32x32p(t_o + c * 32, o);
         tmem_ld_wait();
@@ -496,36 +435,24 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
   int rc = cached_tmap(&tm, VB200_BF16, qkv_bf16, static_cast<uint64_t>(3) * d, M,
                        static_cast<uint64_t>(3) * d * 2, HD, 128);
   if (rc != VB200_OK) return rc;
-  // bring-up knob: VB200_ATTN_VARIANT = bit0 speculative single-pass softmax (SPLIT 1 only), bit1 S-first
-  // issue order, bit2 two warps per row quadrant (SPLIT 2)
-  static int variant = -1;
-  if (variant < 0) {
+  // A/B knob: VB200_ATTN_VARIANT=0 selects the classic schedule, anything else early release
+  static int mode = -1;
+  if (mode < 0) {
     const char* e = getenv("VB200_ATTN_VARIANT");
-    variant = e ? atoi(e) & 7 : 2;
+    mode = (e && atoi(e) == 0) ? 0 : 1;
   }
   dim3 grid((max_T + 2 * BQ - 1) / (2 * BQ), n_heads, B);
   const float sl2 = scale * 1.4426950408889634f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
-#define VB_ATTN_LAUNCH(SP, SF, SL)                                                                      \
-  do {                                                                                                  \
-    static bool configured = false;                                                                     \
-    if (!configured) {                                                                                  \
-      VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<SP, SF, SL>,                                 \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));     \
-      configured = true;                                                                                \
-    }                                                                                                   \
-    flash_attn_kernel<SP, SF, SL><<<grid, (2 + 8 * SL) * 32, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2); \
-  } while (0)
-  switch (variant) {
-    case 0: VB_ATTN_LAUNCH(false, false, 1); break;
-    case 1: VB_ATTN_LAUNCH(true, false, 1); break;
-    case 2: VB_ATTN_LAUNCH(false, true, 1); break;
-    case 3: VB_ATTN_LAUNCH(true, true, 1); break;
-    case 4: case 5: VB_ATTN_LAUNCH(false, false, 2); break;
-    default: VB_ATTN_LAUNCH(false, true, 2); break;
+  static bool configured = false;
+  if (!configured) {
+    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    configured = true;
   }
-#undef VB_ATTN_LAUNCH
+  if (mode == 0) flash_attn_kernel<0><<<grid, THREADS, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);
+  else flash_attn_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

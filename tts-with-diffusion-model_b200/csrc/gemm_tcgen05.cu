@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_out);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * 32); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);     // one arrival per epilogue warp
     }
     if (lane == 0) tma_store_wait_all();
   }
