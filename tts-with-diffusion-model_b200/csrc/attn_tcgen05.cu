@@ -2,29 +2,25 @@
 // base.py:112-127 materialises (b, i, j, h) scores + mask + softmax in HBM).
 //
 // One CTA = (utterance, head, PAIR of 128-query tiles A/B); it walks the utterance's keys in
-// blocks of 128.  12 warps:
+// blocks of 128 and keeps the tensor pipe busy by ping-ponging the two tiles.  12 warps:
 //   warp 0 lane 0 : TMA producer  — Q_A, Q_B once, then K/V blocks through a 3-stage ring
 //   warp 1 lane 0 : MMA issuer    — S_X = Q_X K^T   (tcgen05.mma 128xNx16, SS, both K-major)
 //                                   O_X += P_X V    (128x64x16, A = P_X from TMEM, B = V straight
 //                                                    from the TMA tile as an MN-major operand)
-//   warps 4..7    : softmax of tile A, warps 8..11: softmax of tile B — thread = one query row.
-// Measured on B200: the softmax -> MMA -> softmax round trip (mbarrier hops + MMA latency) costs
-// ~900 cycles per hop pair, more than the MMAs themselves, so the dependency chain has to be
-// taken off the critical path ("early release", MODE 1): a softmax thread pulls all 128 scores of
-// its row into registers with ONE pass of tcgen05.ld and immediately signals s_free; the MMA warp
-// issues S_X(j+1) right then, i.e. a whole softmax block (~1000 cycles) ahead of its use.  The
-// 128 live scores need ~190 registers, so the control warpgroup gives its registers away
-// (setmaxnreg.dec 88) and the two softmax warpgroups grow to 200 (setmaxnreg.inc).
-// P (bf16) goes to its own TMEM columns and feeds O_X += P_X V; O accumulates in TMEM across key
-// blocks (fp32) and is rescaled only when the row max grows by more than 2^8 (exact: the common
-// factor cancels in O / l).  TMEM (512 columns): S_A 128 | S_B 128 | P_A 64 | P_B 64 | O_A 64 | O_B 64.
+//   warps 4..7    : softmax of tile A, warps 8..11: softmax of tile B — thread = one query row:
+//                   tcgen05.ld of the 128 scores (max pass, then exp2 pass against a lazily updated
+//                   reference max); P (bf16) goes to its own TMEM columns and S_X is released
+//                   (s_free) as soon as its last 64 columns sit in registers, so the MMA warp issues
+//                   S_X(j+1) half an exp pass before P_X(j) V_j.
+// O accumulates in TMEM across key blocks (fp32); it is rescaled only when the row max grows by
+// more than 2^8 (exact: the common factor cancels in O / l), so the steady state has no TMEM round
+// trip for O.  TMEM (512 columns): S_A 128 | S_B 128 | P_A 64 | P_B 64 | O_A 64 | O_B 64.
 // Keys past the utterance end are masked to -inf — the reference's key-padding mask
 // (base.py:119-124) in the packed-row layout — and the last key block only issues the MMAs
 // (N resp. K rounded up to 16) its valid keys need.
-// MODE 0 keeps the first validated schedule (two tcgen05.ld passes, S_X(j+1) issued when P_X(j) is
-// written) for A/B measurements: VB200_ATTN_VARIANT=0.
-#include <stdlib.h>
-
+// Measured (profiles/): the kernel is bound by the softmax -> MMA -> softmax dependency chain
+// (mbarrier hops + MMA latency, ~900 cycles per block), not by MUFU or the tensor pipe: removing
+// the exponentials does not change its time.  DESIGN.md §4 lists what was tried against that.
 #include "common.cuh"
 
 namespace vb200 {
@@ -35,8 +31,7 @@ constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: 128 rows x 128 B
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;   // S_X at 128*X, P_X at 256+64*X, O_X at 384+64*X
 constexpr int THREADS = 12 * 32;          // control warpgroup + two softmax warpgroups
-constexpr int THREADS_SPLIT = 20 * 32;    // MODE 2: control warpgroup + four softmax warpgroups
-constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256 + 2 * 512 * 4;
+constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
 constexpr float RESCALE_LOG2 = 8.0f;
 }  // namespace attn
 
@@ -155,100 +150,11 @@ __device__ __forceinline__ void update_reference(float bm, int j, float scale_lo
   }
 }
 
-// MODE 1: one key block of one query row, scores held in registers, S_x released before the math.
-template <bool TAIL>
-__device__ __forceinline__ void softmax_block_early(uint32_t t_s, uint32_t t_p, uint32_t t_o, uint64_t* pv_done_x,
-                                                    uint64_t* s_free_x, int j, int n_chunks, int last_valid,
-                                                    float scale_log2, int lane, float& m_ref, float& l) {
-  uint32_t s0[32], s1[32], s2[32], s3[32];       // four named arrays: keeps all 128 scores in registers
-  const bool a1 = !TAIL || n_chunks > 1, a2 = !TAIL || n_chunks > 2, a3 = !TAIL || n_chunks > 3;
-  tmem_ld_32x32p(t_s, s0);
-  if (a1) tmem_ld_32x32p(t_s + 32, s1);
-  if (a2) tmem_ld_32x32p(t_s + 64, s2);
-  if (a3) tmem_ld_32x32p(t_s + 96, s3);
-  tmem_ld_wait();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(s_free_x);                   // S_x(j) is in registers: S_x(j+1) may be issued
-  float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-  max_chunk<TAIL>(s0, 0, last_valid, bm);
-  if (a1) max_chunk<TAIL>(s1, 32, last_valid, bm);
-  if (a2) max_chunk<TAIL>(s2, 64, last_valid, bm);
-  if (a3) max_chunk<TAIL>(s3, 96, last_valid, bm);
-  update_reference(fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3])), j, scale_log2, t_o, pv_done_x, m_ref, l);
-  float mneg = -m_ref * scale_log2;
-  float ps[4] = {0.f, 0.f, 0.f, 0.f};
-  // the empty asm statements order the four chunks for the scheduler: without them all 128
-  // exponentials are hoisted ahead of the packing and the live range doubles
-  exp_store_chunk(s0, t_p, scale_log2, mneg, ps, j > 0 ? pv_done_x : nullptr, (j - 1) & 1);
-  asm volatile("" : "+f"(mneg));
-  if (a1) exp_store_chunk(s1, t_p + 16, scale_log2, mneg, ps, nullptr, 0);
-  asm volatile("" : "+f"(mneg));
-  if (a2) exp_store_chunk(s2, t_p + 32, scale_log2, mneg, ps, nullptr, 0);
-  asm volatile("" : "+f"(mneg));
-  if (a3) exp_store_chunk(s3, t_p + 48, scale_log2, mneg, ps, nullptr, 0);
-  l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
-}
-
-// MODE 2: the 128 scores of a row are shared by two threads (same TMEM lane, warps with the same
-// warp % 4), 64 columns each, so the early release of MODE 1 needs only 64 live scores per thread
-// (no spills at ~110 registers) and four softmax warps per scheduler hide MUFU / TMEM latency.
-// The two threads exchange their partial row maxima through shared memory and a 64-thread named
-// barrier, so both use the same reference max; row sums are combined once, in the epilogue.
-template <bool TAIL>
-__device__ __forceinline__ void softmax_block_split(uint32_t t_s, uint32_t t_p, uint32_t t_o, uint64_t* pv_done_x,
-                                                    uint64_t* s_free_x, int j, int n_chunks, int last_valid,
-                                                    float scale_log2, int hh, int r_tile, int lane, float* xm,
-                                                    int bar_id, float& m_ref, float& l) {
-  using namespace attn;
-  uint32_t sa[32], sb[32];
-  const bool act0 = !TAIL || hh * 2 < n_chunks, act1 = !TAIL || hh * 2 + 1 < n_chunks;
-  if (act0) tmem_ld_32x32p(t_s + hh * 64, sa);
-  if (act1) tmem_ld_32x32p(t_s + hh * 64 + 32, sb);
-  tmem_ld_wait();
-  tc_fence_before();
-  __syncwarp();
-  if (lane == 0) mbar_arrive(s_free_x);                   // S_x(j) is in registers: S_x(j+1) may be issued
-  float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-  if (act0) max_chunk<TAIL>(sa, hh * 64, last_valid, bm);
-  if (act1) max_chunk<TAIL>(sb, hh * 64 + 32, last_valid, bm);
-  float bmx = fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3]));
-  xm[hh * 128 + r_tile] = bmx;
-  asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-  bmx = fmaxf(bmx, xm[(hh ^ 1) * 128 + r_tile]);          // identical in both threads of the row
-  if (j == 0) {
-    m_ref = bmx;
-  } else {
-    const bool need = (bmx - m_ref) * scale_log2 > RESCALE_LOG2;
-    if (__any_sync(0xffffffffu, need)) {
-      mbar_wait(pv_done_x, (j - 1) & 1);                  // O_x quiescent: PV_x(j-1) retired
-      tc_fence_after();
-      const float alpha = need ? ex2_approx((m_ref - bmx) * scale_log2) : 1.0f;
-      if (need) { m_ref = bmx; l *= alpha; }
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {                       // this thread rescales 32 of the 64 O columns
-        uint32_t o[16];
-        tmem_ld_32x16(t_o + hh * 32 + c * 16, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-        tmem_st_32x16(t_o + hh * 32 + c * 16, o);
-      }
-    }
-  }
-  float mneg = -m_ref * scale_log2;
-  float ps[4] = {0.f, 0.f, 0.f, 0.f};
-  if (act0) exp_store_chunk(sa, t_p + hh * 32, scale_log2, mneg, ps, j > 0 ? pv_done_x : nullptr, (j - 1) & 1);
-  asm volatile("" : "+f"(mneg));
-  if (act1) exp_store_chunk(sb, t_p + hh * 32 + 16, scale_log2, mneg, ps, (!act0 && j > 0) ? pv_done_x : nullptr, (j - 1) & 1);
-  l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
-}
-
-// MODE 0: two passes over S_x in TMEM (max, then exp), 32 columns at a time.
+// One key block of one query row: two passes over S_x in TMEM (max, then exp), 32 columns at a time.
 template <bool TAIL>
 __device__ __forceinline__ void softmax_block_classic(uint32_t t_s, uint32_t t_p, uint32_t t_o, uint64_t* pv_done_x,
-                                                      int j, int n_chunks, int last_valid, float scale_log2,
-                                                      float& m_ref, float& l) {
+                                                      uint64_t* s_free_x, int lane, int j, int n_chunks,
+                                                      int last_valid, float scale_log2, float& m_ref, float& l) {
   float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
@@ -259,23 +165,53 @@ __device__ __forceinline__ void softmax_block_classic(uint32_t t_s, uint32_t t_p
     max_chunk<TAIL>(s, c * 32, last_valid, bm);
   }
   update_reference(fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3])), j, scale_log2, t_o, pv_done_x, m_ref, l);
-  const float mneg = -m_ref * scale_log2;
+  float mneg = -m_ref * scale_log2;
   float ps[4] = {0.f, 0.f, 0.f, 0.f};
   float unused[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    if (TAIL && c >= n_chunks) break;
-    uint32_t s[32];
-    tmem_ld_32x32p(t_s + c * 32, s);
+  const uint32_t prev = (j - 1) & 1;
+  if (!TAIL) {
+    // chunks 0 and 1 straight from TMEM; chunks 2 and 3 are pulled into registers together, which is
+    // the last read of S_x(j): s_free lets the MMA warp issue S_x(j+1) half an exp pass early
+    {
+      uint32_t s[32];
+      tmem_ld_32x32p(t_s, s);
+      tmem_ld_wait();
+      exp_store_chunk(s, t_p, scale_log2, mneg, ps, j > 0 ? pv_done_x : nullptr, prev);
+    }
+    {
+      uint32_t s[32];
+      tmem_ld_32x32p(t_s + 32, s);
+      tmem_ld_wait();
+      exp_store_chunk(s, t_p + 16, scale_log2, mneg, ps, nullptr, 0);
+    }
+    uint32_t s2[32], s3[32];
+    tmem_ld_32x32p(t_s + 64, s2);
+    tmem_ld_32x32p(t_s + 96, s3);
     tmem_ld_wait();
-    if (TAIL) max_chunk<true>(s, c * 32, last_valid, unused);     // re-apply the key mask
-    exp_store_chunk(s, t_p + c * 16, scale_log2, mneg, ps, (c == 0 && j > 0) ? pv_done_x : nullptr, (j - 1) & 1);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(s_free_x);
+    exp_store_chunk(s2, t_p + 32, scale_log2, mneg, ps, nullptr, 0);
+    asm volatile("" : "+f"(mneg));                        // keep the two chunks in order (register peak)
+    exp_store_chunk(s3, t_p + 48, scale_log2, mneg, ps, nullptr, 0);
+  } else {
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      if (c >= n_chunks) break;
+      uint32_t s[32];
+      tmem_ld_32x32p(t_s + c * 32, s);
+      tmem_ld_wait();
+      max_chunk<true>(s, c * 32, last_valid, unused);     // re-apply the key mask
+      exp_store_chunk(s, t_p + c * 16, scale_log2, mneg, ps, (c == 0 && j > 0) ? pv_done_x : nullptr, prev);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(s_free_x);
   }
   l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(MODE == 2 ? attn::THREADS_SPLIT : attn::THREADS, 1) flash_attn_kernel(
+__global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
     const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
     const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
   using namespace attn;
@@ -301,10 +237,8 @@ __global__ void __launch_bounds__(MODE == 2 ? attn::THREADS_SPLIT : attn::THREAD
   uint64_t* s_full = kv_empty + KV_STAGES;        // [2]  S_X(j) complete
   uint64_t* p_full = s_full + 2;                  // [2]  P_X(j) written (one arrival per softmax warp)
   uint64_t* pv_done = p_full + 2;                 // [2]  O_X += P_X(j) V_j retired
-  uint64_t* s_free = pv_done + 2;                 // [2]  MODE 1: S_X(j) pulled into registers
+  uint64_t* s_free = pv_done + 2;                 // [2]  last read of S_X(j) done (one arrival per softmax warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
-  float* xch = reinterpret_cast<float*>(bars + 32);   // MODE 2: [tile][parity][half][128] row maxima / sums
-  constexpr int WPT = MODE == 2 ? 8 : 4;              // softmax warps per tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -313,7 +247,7 @@ __global__ void __launch_bounds__(MODE == 2 ? attn::THREADS_SPLIT : attn::THREAD
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1); mbar_init(&p_full[x], WPT); mbar_init(&pv_done[x], 1); mbar_init(&s_free[x], WPT);
+      mbar_init(&s_full[x], 1); mbar_init(&p_full[x], 4); mbar_init(&pv_done[x], 1); mbar_init(&s_free[x], 4);
     }
     fence_barrier_init();
   }
@@ -328,8 +262,6 @@ __global__ void __launch_bounds__(MODE == 2 ? attn::THREADS_SPLIT : attn::THREAD
 
   if (warp < 4) {
     // ============================================================== control warpgroup
-    if (MODE == 1) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    if (MODE == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     if (warp == 0 && lane == 0) {
       // ---------------------------------------------------------- TMA producer
       mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
@@ -387,36 +319,22 @@ __global__ void __launch_bounds__(MODE == 2 ? attn::THREADS_SPLIT : attn::THREAD
       for (int j = 0; j < nblk; ++j) {
         const bool more = j + 1 < nblk;
         if (more) mbar_wait(&kv_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
-        if (MODE >= 1) {
-          // early release: S_x(j+1) as soon as S_x(j) sits in the softmax registers, P_x(j) V_j later
-          if (more)
-            for (int x = 0; x < n_tiles; ++x) {
-              mbar_wait(&s_free[x], j & 1);
-              tc_fence_after();
-              issue_s(x, j + 1);
-            }
-          for (int x = 0; x < n_tiles; ++x) {
-            mbar_wait(&p_full[x], j & 1);
-            tc_fence_after();
-            issue_pv(x, j);
+        for (int x = 0; x < n_tiles; ++x) {
+          if (more) {
+            mbar_wait(&s_free[x], j & 1);                // S_x(j) fully read: next scores first,
+            tc_fence_after();                            // the softmax warps wait on these
+            issue_s(x, j + 1);
           }
-        } else {
-          for (int x = 0; x < n_tiles; ++x) {
-            mbar_wait(&p_full[x], j & 1);                // P_x(j) in TMEM, S_x consumed, O_x rescaled if needed
-            tc_fence_after();
-            if (more) issue_s(x, j + 1);                 // next scores first: the softmax warps wait on these
-            issue_pv(x, j);
-          }
+          mbar_wait(&p_full[x], j & 1);                  // P_x(j) in TMEM, O_x rescaled if needed
+          tc_fence_after();
+          issue_pv(x, j);
         }
         umma_commit(&kv_empty[j % KV_STAGES]);           // K_j / V_j consumed by both tiles
       }
     }
   } else {
     // ============================================================== softmax / output warpgroups
-    if (MODE == 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    if (MODE == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-    const int x = (warp - 4) / WPT;                    // 0: tile A, 1: tile B
-    const int hh = MODE == 2 ? ((warp - 4) >> 2) & 1 : 0;   // MODE 2: which 64-column share of the row
+    const int x = (warp - 4) >> 2;                     // 0: tile A, 1: tile B
     if (x == 0 || has_b) {
       const int quad = warp & 3;
       const int r_tile = quad * 32 + lane;             // query row inside the tile
@@ -425,25 +343,14 @@ __global__ void __launch_bounds__(MODE == 2 ? attn::THREADS_SPLIT : attn::THREAD
       const uint32_t t_p = tmem_base + lane_off + COL_P + x * 64;
       const uint32_t t_o = tmem_base + lane_off + COL_O + x * 64;
       float m_ref = -INFINITY, l = 0.f;
-      float* xch_t = xch + x * 512;                    // [parity][half][128]
-      const int bar_id = 1 + x * 4 + quad;             // named barrier of the two warps sharing these rows
 
       for (int j = 0; j < nblk; ++j) {
         const bool tail = (j == nblk - 1) && last_valid < BKV;
         const int n_chunks = tail ? (last_n + 31) / 32 : 4;
         mbar_wait(&s_full[x], j & 1);
         tc_fence_after();
-        if (MODE == 2) {
-          float* xm = xch_t + (j & 1) * 256;
-          if (!tail) softmax_block_split<false>(t_s, t_p, t_o, &pv_done[x], &s_free[x], j, 4, BKV, scale_log2, hh, r_tile, lane, xm, bar_id, m_ref, l);
-          else softmax_block_split<true>(t_s, t_p, t_o, &pv_done[x], &s_free[x], j, n_chunks, last_valid, scale_log2, hh, r_tile, lane, xm, bar_id, m_ref, l);
-        } else if (MODE == 1) {
-          if (!tail) softmax_block_early<false>(t_s, t_p, t_o, &pv_done[x], &s_free[x], j, 4, BKV, scale_log2, lane, m_ref, l);
-          else softmax_block_early<true>(t_s, t_p, t_o, &pv_done[x], &s_free[x], j, n_chunks, last_valid, scale_log2, lane, m_ref, l);
-        } else {
-          if (!tail) softmax_block_classic<false>(t_s, t_p, t_o, &pv_done[x], j, 4, BKV, scale_log2, m_ref, l);
-          else softmax_block_classic<true>(t_s, t_p, t_o, &pv_done[x], j, n_chunks, last_valid, scale_log2, m_ref, l);
-        }
+        if (!tail) softmax_block_classic<false>(t_s, t_p, t_o, &pv_done[x], &s_free[x], lane, j, 4, BKV, scale_log2, m_ref, l);
+        else softmax_block_classic<true>(t_s, t_p, t_o, &pv_done[x], &s_free[x], lane, j, n_chunks, last_valid, scale_log2, m_ref, l);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
@@ -453,17 +360,10 @@ __global__ void __launch_bounds__(MODE == 2 ? attn::THREADS_SPLIT : attn::THREAD
       mbar_wait(&pv_done[x], (nblk - 1) & 1);
       tc_fence_after();
       const int q_row = (qp * 2 + x) * BQ + r_tile;
-      if (MODE == 2) {                                 // total row sum = both column shares
-        float* xl = xch_t + (nblk & 1) * 256;
-        xl[hh * 128 + r_tile] = l;
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-        l += xl[(hh ^ 1) * 128 + r_tile];
-      }
       const float inv = 1.0f / l;
       __nv_bfloat16* o_dst = out + static_cast<size_t>(row0 + q_row) * d + h * HD;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        if (MODE == 2 && c != hh) continue;            // each of the two warps stores 32 of the 64 columns
         uint32_t o[32];
         tmem_ld_32x32p(t_o + c * 32, o);
         tmem_ld_wait();
@@ -508,28 +408,16 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
   int rc = cached_tmap(&tm, VB200_BF16, qkv_bf16, static_cast<uint64_t>(3) * d, M,
                        static_cast<uint64_t>(3) * d * 2, HD, 128);
   if (rc != VB200_OK) return rc;
-  // A/B knob: VB200_ATTN_VARIANT=1 selects the early-release schedule (measured slower so far:
-  // 128 live scores spill at the 200-register budget), default is the classic schedule
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("VB200_ATTN_VARIANT");
-    mode = e ? atoi(e) : 0;
-    if (mode < 0 || mode > 2) mode = 0;
-  }
   dim3 grid((max_T + 2 * BQ - 1) / (2 * BQ), n_heads, B);
   const float sl2 = scale * 1.4426950408889634f;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
   static bool configured = false;
   if (!configured) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  if (mode == 0) flash_attn_kernel<0><<<grid, THREADS, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);
-  else if (mode == 1) flash_attn_kernel<1><<<grid, THREADS, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);
-  else flash_attn_kernel<2><<<grid, THREADS_SPLIT, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);
+  flash_attn_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
