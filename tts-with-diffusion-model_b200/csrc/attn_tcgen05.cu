@@ -33,6 +33,7 @@ constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;   // S_X at 128*X, P_X a
 constexpr int THREADS = 12 * 32;          // control warpgroup + two softmax warpgroups
 constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
 constexpr float RESCALE_LOG2 = 8.0f;
+constexpr int TAIL_ROWS_MAX = 32;         // <= this many rows left over after the 256-row pairs go to the tail kernel
 }  // namespace attn
 
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -211,6 +212,84 @@ __device__ __forceinline__ void softmax_block_classic(uint32_t t_s, uint32_t t_p
   l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
 }
 
+// Query rows left over after the 256-row tile pairs (T mod 256, when that is <= TAIL_ROWS_MAX): a
+// tile pair for, say, the last 3 of 1027 rows costs as much as a full one, so those rows are done
+// on CUDA cores instead — one warp per (row, head), keys striped over the lanes, online softmax per
+// lane, one cross-lane merge at the end.  ~0.3 % of the attention work at T = 1027.
+__global__ void __launch_bounds__(128) attn_tail_rows_kernel(
+    __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ qkv,
+    const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
+  using namespace attn;
+  const int b = blockIdx.y, h = blockIdx.x;
+  const int row0 = cu_rows[b];
+  const int T = cu_rows[b + 1] - row0;
+  const int left = T % (2 * BQ);
+  if (left == 0 || left > TAIL_ROWS_MAX) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int d = n_heads * HD;
+  const size_t ld = static_cast<size_t>(3) * d;
+  for (int r = warp; r < left; r += 4) {
+    const size_t row = static_cast<size_t>(row0 + T - left + r);
+    float q[HD];
+    {
+      const uint4* qp4 = reinterpret_cast<const uint4*>(qkv + row * ld + h * HD);
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const uint4 w = __ldg(qp4 + c);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          q[c * 8 + 2 * i] = __uint_as_float(ww[i] << 16) * scale_log2;
+          q[c * 8 + 2 * i + 1] = __uint_as_float(ww[i] & 0xffff0000u) * scale_log2;
+        }
+      }
+    }
+    float m = -INFINITY, l = 0.f, o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const uint4* kp = reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(row0 + j) * ld + d + h * HD);
+      const uint4* vp = reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(row0 + j) * ld + 2 * d + h * HD);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const uint4 w = __ldg(kp + c);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          s = fmaf(q[c * 8 + 2 * i], __uint_as_float(ww[i] << 16), s);
+          s = fmaf(q[c * 8 + 2 * i + 1], __uint_as_float(ww[i] & 0xffff0000u), s);
+        }
+      }
+      const float m_new = fmaxf(m, s);
+      const float corr = ex2_approx(m - m_new), p = ex2_approx(s - m_new);
+      l = fmaf(l, corr, p);
+      m = m_new;
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const uint4 w = __ldg(vp + c);
+        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          o[c * 8 + 2 * i] = fmaf(o[c * 8 + 2 * i], corr, p * __uint_as_float(ww[i] << 16));
+          o[c * 8 + 2 * i + 1] = fmaf(o[c * 8 + 2 * i + 1], corr, p * __uint_as_float(ww[i] & 0xffff0000u));
+        }
+      }
+    }
+    // merge the 32 per-lane partial softmaxes
+    const float M = warp_max(m);
+    const float corr = ex2_approx(m - M);               // 0 for lanes that saw no key
+    const float inv = 1.0f / warp_sum(l * corr);
+    float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD; ++i) {
+      const float v = warp_sum(o[i] * corr) * inv;
+      if ((i >> 1) == lane) { if (i & 1) r1 = v; else r0 = v; }
+    }
+    *reinterpret_cast<uint32_t*>(out + row * d + h * HD + 2 * lane) = pack_bf16x2(r0, r1);
+  }
+}
+
 __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
     const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
     const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
@@ -218,8 +297,10 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
   const int b = blockIdx.z, h = blockIdx.y, qp = blockIdx.x;
   const int row0 = cu_rows[b];
   const int T = cu_rows[b + 1] - row0;
-  if (qp * 2 * BQ >= T) return;                   // uniform early exit, before any allocation
-  const bool has_b = qp * 2 * BQ + BQ < T;        // second tile of the pair holds valid rows
+  const int left = T % (2 * BQ);
+  const int T_q = (left > 0 && left <= TAIL_ROWS_MAX) ? T - left : T;   // query rows of the tile pairs
+  if (qp * 2 * BQ >= T_q) return;                 // uniform early exit, before any allocation
+  const bool has_b = qp * 2 * BQ + BQ < T_q;      // second tile of the pair holds valid rows
   const int nblk = (T + BKV - 1) / BKV;
   const int last_valid = T - (nblk - 1) * BKV;    // keys inside the utterance in the last block
   const int last_n = (last_valid + 15) & ~15;     // MMA extent of the last block (multiple of 16)
@@ -418,6 +499,8 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
     configured = true;
   }
   flash_attn_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);
+  attn_tail_rows_kernel<<<dim3(n_heads, B), 128, 0, st>>>(o, static_cast<const __nv_bfloat16*>(qkv_bf16), cu_rows,
+                                                          n_heads, sl2);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
