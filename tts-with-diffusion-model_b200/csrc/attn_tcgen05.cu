@@ -214,12 +214,16 @@ __device__ __forceinline__ void softmax_block_classic(uint32_t t_s, uint32_t t_p
 
 // Query rows left over after the 256-row tile pairs (T mod 256, when that is <= TAIL_ROWS_MAX): a
 // tile pair for, say, the last 3 of 1027 rows costs as much as a full one, so those rows are done
-// on CUDA cores instead — one warp per (row, head), keys striped over the lanes, online softmax per
-// lane, one cross-lane merge at the end.  ~0.3 % of the attention work at T = 1027.
+// on CUDA cores instead.  One warp per (row, head), exact two-pass softmax:
+//   phase 1  lanes over keys: s_j = q . k_j (eight 16-byte loads per key, independent across keys),
+//            scores parked in shared memory, warp max / sum of exp2
+//   phase 2  lanes over head dims: o[d] = sum_j p_j v_j[d], one coalesced 128-byte row of V per key.
+// ~0.3 % of the attention work at T = 1027.
 __global__ void __launch_bounds__(128) attn_tail_rows_kernel(
     __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ qkv,
-    const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
+    const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2, int max_T) {
   using namespace attn;
+  extern __shared__ float tail_p[];                    // [4 warps][max_T]
   const int b = blockIdx.y, h = blockIdx.x;
   const int row0 = cu_rows[b];
   const int T = cu_rows[b + 1] - row0;
@@ -228,6 +232,9 @@ __global__ void __launch_bounds__(128) attn_tail_rows_kernel(
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int d = n_heads * HD;
   const size_t ld = static_cast<size_t>(3) * d;
+  float* p = tail_p + static_cast<size_t>(warp) * max_T;
+  const __nv_bfloat16* kbase = qkv + static_cast<size_t>(row0) * ld + d + h * HD;
+  const __nv_bfloat16* vbase = kbase + d;
   for (int r = warp; r < left; r += 4) {
     const size_t row = static_cast<size_t>(row0 + T - left + r);
     float q[HD];
@@ -244,49 +251,62 @@ __global__ void __launch_bounds__(128) attn_tail_rows_kernel(
         }
       }
     }
-    float m = -INFINITY, l = 0.f, o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    // phase 1: scores (log2 domain) and their max
+    float m = -INFINITY;
+#pragma unroll 2
     for (int j = lane; j < T; j += 32) {
-      const uint4* kp = reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(row0 + j) * ld + d + h * HD);
-      const uint4* vp = reinterpret_cast<const uint4*>(qkv + static_cast<size_t>(row0 + j) * ld + 2 * d + h * HD);
-      float s = 0.f;
+      const uint4* kp = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * ld);
+      uint4 w[HD / 8];
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) w[c] = __ldg(kp + c);
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
       for (int c = 0; c < HD / 8; ++c) {
-        const uint4 w = __ldg(kp + c);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+        const uint32_t ww[4] = {w[c].x, w[c].y, w[c].z, w[c].w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          s = fmaf(q[c * 8 + 2 * i], __uint_as_float(ww[i] << 16), s);
-          s = fmaf(q[c * 8 + 2 * i + 1], __uint_as_float(ww[i] & 0xffff0000u), s);
+          s0 = fmaf(q[c * 8 + 2 * i], __uint_as_float(ww[i] << 16), s0);
+          s1 = fmaf(q[c * 8 + 2 * i + 1], __uint_as_float(ww[i] & 0xffff0000u), s1);
         }
       }
-      const float m_new = fmaxf(m, s);
-      const float corr = ex2_approx(m - m_new), p = ex2_approx(s - m_new);
-      l = fmaf(l, corr, p);
-      m = m_new;
+      const float sc = s0 + s1;
+      p[j] = sc;
+      m = fmaxf(m, sc);
+    }
+    m = warp_max(m);
+    float l = 0.f;
+    for (int j = lane; j < T; j += 32) {
+      const float e = ex2_approx(p[j] - m);
+      p[j] = e;
+      l += e;
+    }
+    l = warp_sum(l);
+    __syncwarp();
+    // phase 2: lane owns head dims 2*lane, 2*lane+1
+    float a0 = 0.f, a1 = 0.f;
+    const uint32_t* vp = reinterpret_cast<const uint32_t*>(vbase) + lane;
+    const size_t ldw = ld / 2;                          // row stride in 32-bit words
+    int j = 0;
+    for (; j + 8 <= T; j += 8) {
+      uint32_t v[8];
 #pragma unroll
-      for (int c = 0; c < HD / 8; ++c) {
-        const uint4 w = __ldg(vp + c);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(vp + static_cast<size_t>(j + u) * ldw);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          o[c * 8 + 2 * i] = fmaf(o[c * 8 + 2 * i], corr, p * __uint_as_float(ww[i] << 16));
-          o[c * 8 + 2 * i + 1] = fmaf(o[c * 8 + 2 * i + 1], corr, p * __uint_as_float(ww[i] & 0xffff0000u));
-        }
+      for (int u = 0; u < 8; ++u) {
+        const float pj = p[j + u];
+        a0 = fmaf(pj, __uint_as_float(v[u] << 16), a0);
+        a1 = fmaf(pj, __uint_as_float(v[u] & 0xffff0000u), a1);
       }
     }
-    // merge the 32 per-lane partial softmaxes
-    const float M = warp_max(m);
-    const float corr = ex2_approx(m - M);               // 0 for lanes that saw no key
-    const float inv = 1.0f / warp_sum(l * corr);
-    float r0 = 0.f, r1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < HD; ++i) {
-      const float v = warp_sum(o[i] * corr) * inv;
-      if ((i >> 1) == lane) { if (i & 1) r1 = v; else r0 = v; }
+    for (; j < T; ++j) {
+      const uint32_t v = __ldg(vp + static_cast<size_t>(j) * ldw);
+      const float pj = p[j];
+      a0 = fmaf(pj, __uint_as_float(v << 16), a0);
+      a1 = fmaf(pj, __uint_as_float(v & 0xffff0000u), a1);
     }
-    *reinterpret_cast<uint32_t*>(out + row * d + h * HD + 2 * lane) = pack_bf16x2(r0, r1);
+    const float inv = 1.0f / l;
+    *reinterpret_cast<uint32_t*>(out + row * d + h * HD + 2 * lane) = pack_bf16x2(a0 * inv, a1 * inv);
+    __syncwarp();
   }
 }
 
@@ -499,8 +519,16 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
     configured = true;
   }
   flash_attn_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);
-  attn_tail_rows_kernel<<<dim3(n_heads, B), 128, 0, st>>>(o, static_cast<const __nv_bfloat16*>(qkv_bf16), cu_rows,
-                                                          n_heads, sl2);
+  const size_t tail_smem = static_cast<size_t>(4) * max_T * sizeof(float);
+  VB_REQUIRE(tail_smem <= 200 * 1024, "flash_attn: max_T=%d too long for the tail-rows kernel", max_T);
+  static size_t tail_smem_set = 48 * 1024;
+  if (tail_smem > tail_smem_set) {
+    VB_CHECK_CUDA(cudaFuncSetAttribute(attn_tail_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(tail_smem)));
+    tail_smem_set = tail_smem;
+  }
+  attn_tail_rows_kernel<<<dim3(n_heads, B), 128, tail_smem, st>>>(
+      o, static_cast<const __nv_bfloat16*>(qkv_bf16), cu_rows, n_heads, sl2, max_T);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
