@@ -33,7 +33,6 @@ constexpr uint32_t COL_S = 0, COL_P = 256, COL_O = 384;   // S_X at 128*X, P_X a
 constexpr int THREADS = 12 * 32;          // control warpgroup + two softmax warpgroups
 constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
 constexpr float RESCALE_LOG2 = 8.0f;
-constexpr int TAIL_ROWS_MAX = 32;         // <= this many rows left over after the 256-row pairs go to the tail kernel
 }  // namespace attn
 
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -212,104 +211,6 @@ __device__ __forceinline__ void softmax_block_classic(uint32_t t_s, uint32_t t_p
   l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
 }
 
-// Query rows left over after the 256-row tile pairs (T mod 256, when that is <= TAIL_ROWS_MAX): a
-// tile pair for, say, the last 3 of 1027 rows costs as much as a full one, so those rows are done
-// on CUDA cores instead.  One warp per (row, head), exact two-pass softmax:
-//   phase 1  lanes over keys: s_j = q . k_j (eight 16-byte loads per key, independent across keys),
-//            scores parked in shared memory, warp max / sum of exp2
-//   phase 2  lanes over head dims: o[d] = sum_j p_j v_j[d], one coalesced 128-byte row of V per key.
-// ~0.3 % of the attention work at T = 1027.
-__global__ void __launch_bounds__(128) attn_tail_rows_kernel(
-    __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ qkv,
-    const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2, int max_T) {
-  using namespace attn;
-  extern __shared__ float tail_p[];                    // [4 warps][max_T]
-  const int b = blockIdx.y, h = blockIdx.x;
-  const int row0 = cu_rows[b];
-  const int T = cu_rows[b + 1] - row0;
-  const int left = T % (2 * BQ);
-  if (left == 0 || left > TAIL_ROWS_MAX) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int d = n_heads * HD;
-  const size_t ld = static_cast<size_t>(3) * d;
-  float* p = tail_p + static_cast<size_t>(warp) * max_T;
-  const __nv_bfloat16* kbase = qkv + static_cast<size_t>(row0) * ld + d + h * HD;
-  const __nv_bfloat16* vbase = kbase + d;
-  for (int r = warp; r < left; r += 4) {
-    const size_t row = static_cast<size_t>(row0 + T - left + r);
-    float q[HD];
-    {
-      const uint4* qp4 = reinterpret_cast<const uint4*>(qkv + row * ld + h * HD);
-#pragma unroll
-      for (int c = 0; c < HD / 8; ++c) {
-        const uint4 w = __ldg(qp4 + c);
-        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          q[c * 8 + 2 * i] = __uint_as_float(ww[i] << 16) * scale_log2;
-          q[c * 8 + 2 * i + 1] = __uint_as_float(ww[i] & 0xffff0000u) * scale_log2;
-        }
-      }
-    }
-    // phase 1: scores (log2 domain) and their max
-    float m = -INFINITY;
-#pragma unroll 2
-    for (int j = lane; j < T; j += 32) {
-      const uint4* kp = reinterpret_cast<const uint4*>(kbase + static_cast<size_t>(j) * ld);
-      uint4 w[HD / 8];
-#pragma unroll
-      for (int c = 0; c < HD / 8; ++c) w[c] = __ldg(kp + c);
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int c = 0; c < HD / 8; ++c) {
-        const uint32_t ww[4] = {w[c].x, w[c].y, w[c].z, w[c].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          s0 = fmaf(q[c * 8 + 2 * i], __uint_as_float(ww[i] << 16), s0);
-          s1 = fmaf(q[c * 8 + 2 * i + 1], __uint_as_float(ww[i] & 0xffff0000u), s1);
-        }
-      }
-      const float sc = s0 + s1;
-      p[j] = sc;
-      m = fmaxf(m, sc);
-    }
-    m = warp_max(m);
-    float l = 0.f;
-    for (int j = lane; j < T; j += 32) {
-      const float e = ex2_approx(p[j] - m);
-      p[j] = e;
-      l += e;
-    }
-    l = warp_sum(l);
-    __syncwarp();
-    // phase 2: lane owns head dims 2*lane, 2*lane+1
-    float a0 = 0.f, a1 = 0.f;
-    const uint32_t* vp = reinterpret_cast<const uint32_t*>(vbase) + lane;
-    const size_t ldw = ld / 2;                          // row stride in 32-bit words
-    int j = 0;
-    for (; j + 8 <= T; j += 8) {
-      uint32_t v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(vp + static_cast<size_t>(j + u) * ldw);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float pj = p[j + u];
-        a0 = fmaf(pj, __uint_as_float(v[u] << 16), a0);
-        a1 = fmaf(pj, __uint_as_float(v[u] & 0xffff0000u), a1);
-      }
-    }
-    for (; j < T; ++j) {
-      const uint32_t v = __ldg(vp + static_cast<size_t>(j) * ldw);
-      const float pj = p[j];
-      a0 = fmaf(pj, __uint_as_float(v << 16), a0);
-      a1 = fmaf(pj, __uint_as_float(v & 0xffff0000u), a1);
-    }
-    const float inv = 1.0f / l;
-    *reinterpret_cast<uint32_t*>(out + row * d + h * HD + 2 * lane) = pack_bf16x2(a0 * inv, a1 * inv);
-    __syncwarp();
-  }
-}
-
 __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
     const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
     const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
@@ -317,10 +218,8 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
   const int b = blockIdx.z, h = blockIdx.y, qp = blockIdx.x;
   const int row0 = cu_rows[b];
   const int T = cu_rows[b + 1] - row0;
-  const int left = T % (2 * BQ);
-  const int T_q = (left > 0 && left <= TAIL_ROWS_MAX) ? T - left : T;   // query rows of the tile pairs
-  if (qp * 2 * BQ >= T_q) return;                 // uniform early exit, before any allocation
-  const bool has_b = qp * 2 * BQ + BQ < T_q;      // second tile of the pair holds valid rows
+  if (qp * 2 * BQ >= T) return;                   // uniform early exit, before any allocation
+  const bool has_b = qp * 2 * BQ + BQ < T;        // second tile of the pair holds valid rows
   const int nblk = (T + BKV - 1) / BKV;
   const int last_valid = T - (nblk - 1) * BKV;    // keys inside the utterance in the last block
   const int last_n = (last_valid + 15) & ~15;     // MMA extent of the last block (multiple of 16)
@@ -519,16 +418,6 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
     configured = true;
   }
   flash_attn_kernel<<<grid, THREADS, SMEM_BYTES, st>>>(tm, o, cu_rows, n_heads, sl2);
-  const size_t tail_smem = static_cast<size_t>(4) * max_T * sizeof(float);
-  VB_REQUIRE(tail_smem <= 200 * 1024, "flash_attn: max_T=%d too long for the tail-rows kernel", max_T);
-  static size_t tail_smem_set = 48 * 1024;
-  if (tail_smem > tail_smem_set) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(attn_tail_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(tail_smem)));
-    tail_smem_set = tail_smem;
-  }
-  attn_tail_rows_kernel<<<dim3(n_heads, B), 128, tail_smem, st>>>(
-      o, static_cast<const __nv_bfloat16*>(qkv_bf16), cu_rows, n_heads, sl2, max_T);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

@@ -201,7 +201,7 @@ class DenoiserEngine:
                 hidden_out.append(ws.x.clone())
         L.gather_rows_bf16(ws.head_in, ws.x, lay.resp_row_index)
         gemm(ws.logits, ws.head_in, w.w_cls, w.b_cls, epi=L.EPI_BIAS)
-        self.launches += 1 + 8 * len(w.layers) + 2      # attention = tile-pair kernel + tail-rows kernel
+        self.launches += 1 + 7 * len(w.layers) + 2
         return ws.logits
 
     def _gemm(self, out, A, W, bias=None, residual=None, epi=L.EPI_NONE):
