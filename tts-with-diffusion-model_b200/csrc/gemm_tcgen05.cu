@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
   uint64_t* acc_empty = acc_full + 2;       // [2]     epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
+  const int lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK - 1) / BK;
@@ -86,25 +87,33 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Both control warps run their loops warp-uniformly (all lanes compute the same addresses, one
+  // elected lane executes the TMA / MMA / commit instructions): issuing from a divergent
+  // `if (lane == 0)` region makes the compiler wrap every tcgen05.mma in an elect / R2UR loop.
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------------------ TMA producer
+      const bool leader = elect_one();
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tm_a, &full[stage], kb * BK, m_blk * BM);
-          tma_load_2d(sa + A_BYTES, &tm_b, &full[stage], kb * BK, n_blk * BN);
+          if (leader) {
+            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+            tma_load_2d(sa, &tm_a, &full[stage], kb * BK, m_blk * BM);
+            tma_load_2d(sa + A_BYTES, &tm_b, &full[stage], kb * BK, n_blk * BN);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       // ------------------------------------------------------------ MMA issuer
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, false, false);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
@@ -120,13 +129,17 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t da = umma_desc_kmajor_sw128(sa);
           const uint64_t db = umma_desc_kmajor_sw128(sa + A_BYTES);
+          if (leader) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)   // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
-            umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(&empty[stage]);          // frees the smem slot once these MMAs retire
+            for (int k = 0; k < BK / 16; ++k)   // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
+              umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            umma_commit(&empty[stage]);         // frees the smem slot once these MMAs retire
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&acc_full[as]);            // accumulator complete -> epilogue
+        if (leader) umma_commit(&acc_full[as]); // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {
@@ -140,6 +153,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     constexpr bool kWide = sizeof(OutT) == 4;  // fp32: 32 columns per 128-byte row, else 64
     constexpr int CHUNK_COLS = kWide ? 32 : 64;
     constexpr int CHUNKS = 128 / CHUNK_COLS;
+    const bool epi_leader = elect_one();       // the lane that owns this warp's bulk-store group
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
@@ -152,7 +166,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
         const int n0 = n_blk * BN + half * 128 + c * CHUNK_COLS;
-        if (lane == 0) tma_store_wait_read();  // previous store has finished reading the staging tile
+        if (epi_leader) tma_store_wait_read();  // previous store has finished reading the staging tile
         __syncwarp();
 #pragma unroll
         for (int sub = 0; sub < CHUNK_COLS / 32; ++sub) {
@@ -202,7 +216,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
         }
         fence_proxy_async_smem();              // generic-proxy smem writes -> visible to the TMA engine
         __syncwarp();
-        if (lane == 0 && row0 < M && n0 < N) {
+        if (epi_leader && row0 < M && n0 < N) {
           if (EPI == VB200_EPI_BIAS_RESIDUAL) tma_reduce_add_2d(&tm_out, stage_tile, n0, row0);
           else tma_store_2d(&tm_out, stage_tile, n0, row0);
           tma_store_commit();
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);     // one arrival per epilogue warp
     }
-    if (lane == 0) tma_store_wait_all();
+    if (epi_leader) tma_store_wait_all();
   }
 
   tc_fence_before();
