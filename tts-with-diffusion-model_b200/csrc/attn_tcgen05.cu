@@ -4,7 +4,8 @@
 // One CTA = (utterance, head, PAIR of 128-query tiles A/B); it walks the utterance's keys in
 // blocks of 128.  12 warps:
 //   warp 0 lane 0 : TMA producer  — Q_A, Q_B once, then K/V blocks through a 4-stage ring
-//   warp 1 lane 0 : MMA issuer    — S_X = Q_X K^T   (tcgen05.mma 128xNx16, SS, both K-major)
+//   warps 1, 2    : MMA issuers of tile A / tile B (one elected lane each)
+//                                   S_X = Q_X K^T   (tcgen05.mma 128xNx16, SS, both K-major)
 //                                   O_blk = P_X V   (128x64x16, A = P_X from TMEM, B = V straight
 //                                                    from the TMA tile as an MN-major operand)
 //   warps 4..7    : softmax of tile A, warps 8..11: softmax of tile B — thread = one query row.
@@ -85,16 +86,38 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 
+// exp2 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + r with the 1.5 * 2^23
+// magic constant, 2^r by a cubic on [-0.5, 0.5] (|rel err| < 1.2e-4, far below the bf16 rounding
+// of P), exponent patched in with an integer add.  MUFU.EX2 runs at 16 lanes / clk / SM on B200
+// (tools/mufu_bench.cu), which makes a 128x128 softmax block MUFU-bound at about twice the time of
+// its MMAs; moving a share of the exponentials here rebalances the two pipes (the FA4 trick).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;
+  const float r = x - (t - 12582912.0f);
+  float p = fmaf(r, 0.05550357f, 0.24022650f);
+  p = fmaf(r, p, 0.69314720f);
+  p = fmaf(r, p, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#ifndef VB200_ATTN_EMU_PER_4
+#define VB200_ATTN_EMU_PER_4 0      // exponentials out of every 4 evaluated by ex2_poly instead of MUFU
+#endif
+
 // 32 scores -> 32 probabilities (bf16, 16 TMEM columns); row sum tracked on 4 chains.
 __device__ __forceinline__ void exp_store_chunk(const uint32_t (&s)[32], uint32_t t_p_chunk, float scale_log2,
                                                 float mneg, float (&ps)[4]) {
   uint32_t pk[16];
 #pragma unroll
   for (int i = 0; i < 32; i += 4) {
-    const float p0 = ex2_approx(fmaf(__uint_as_float(s[i]), scale_log2, mneg));
-    const float p1 = ex2_approx(fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg));
-    const float p2 = ex2_approx(fmaf(__uint_as_float(s[i + 2]), scale_log2, mneg));
-    const float p3 = ex2_approx(fmaf(__uint_as_float(s[i + 3]), scale_log2, mneg));
+    const float x0 = fmaf(__uint_as_float(s[i]), scale_log2, mneg);
+    const float x1 = fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg);
+    const float x2 = fmaf(__uint_as_float(s[i + 2]), scale_log2, mneg);
+    const float x3 = fmaf(__uint_as_float(s[i + 3]), scale_log2, mneg);
+    const float p0 = VB200_ATTN_EMU_PER_4 > 3 ? ex2_poly(x0) : ex2_approx(x0);
+    const float p1 = VB200_ATTN_EMU_PER_4 > 1 ? ex2_poly(x1) : ex2_approx(x1);
+    const float p2 = VB200_ATTN_EMU_PER_4 > 2 ? ex2_poly(x2) : ex2_approx(x2);
+    const float p3 = VB200_ATTN_EMU_PER_4 > 0 ? ex2_poly(x3) : ex2_approx(x3);
     ps[0] += p0; ps[1] += p1; ps[2] += p2; ps[3] += p3;
     pk[i >> 1] = pack_bf16x2(p0, p1);
     pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
@@ -225,7 +248,7 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
     mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], has_b ? 2 : 1); }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&buf_free[i], 4);
     }
@@ -267,22 +290,24 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    {
-      // ---------------------------------------------------------- MMA issuer
-      // Everything needed per MMA is a 32-bit add on a precomputed descriptor (smem addresses are
-      // < 2^18, so the 14-bit start-address field of the low word never carries).
+  } else if (warp == 1 || warp == 2) {
+    // ------------------------------------------------------------ MMA issuers, one warp per tile
+    // Tile A and tile B are served by separate warps so that neither tile's MMAs ever wait on the
+    // other tile's softmax: the two softmax pipelines drift apart in phase and share the MUFU pipe
+    // instead of queueing on it in lockstep.  Everything needed per MMA is a 32-bit add on a
+    // precomputed descriptor (smem addresses are < 2^18, so the 14-bit start-address field of the
+    // low word never carries).
+    const int x = warp - 1;
+    if (x == 0 || has_b) {
       const bool leader = elect_one();
       const uint32_t idesc_o = umma_idesc_bf16(BQ, HD, false, true);        // B = V, MN-major
       const uint32_t idesc_s_full = umma_idesc_bf16(BQ, BKV, false, false);
       const uint32_t idesc_s_last = umma_idesc_bf16(BQ, last_n, false, false);
-      const int n_tiles = has_b ? 2 : 1;
-      const uint64_t dq_base = umma_desc_kmajor_sw128(smem_u32(s_q));
+      const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(s_q + x * TILE_BYTES));
       const uint64_t dk_base = umma_desc_kmajor_sw128(smem_u32(s_kv));
       const uint64_t dv_base = umma_desc_mnmajor_sw128(smem_u32(s_kv + TILE_BYTES), 1024);
       constexpr uint32_t kTileStep = TILE_BYTES >> 4;          // descriptor units (16 B)
-      auto issue_s = [&](int x, int j) {      // S_x(j) = Q_x K_j^T into buffer j & 1
-        const uint64_t dq = dq_base + static_cast<uint32_t>(x) * kTileStep;
+      auto issue_s = [&](int j) {             // S_x(j) = Q_x K_j^T into buffer j & 1
         const uint64_t dk = dk_base + static_cast<uint32_t>(j % KV_STAGES) * (2 * kTileStep);
         const uint32_t idesc_s = (j == nblk - 1) ? idesc_s_last : idesc_s_full;
         const int bi = x * 2 + (j & 1);
@@ -294,7 +319,7 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
         }
         __syncwarp();
       };
-      auto issue_pv = [&](int x, int j) {     // O_blk(j) = P_x(j) V_j, inside buffer j & 1
+      auto issue_pv = [&](int j) {            // O_blk(j) = P_x(j) V_j, inside buffer j & 1
         const uint64_t dv = dv_base + static_cast<uint32_t>(j % KV_STAGES) * (2 * kTileStep);
         const int bi = x * 2 + (j & 1);
         const uint32_t t_p = tmem_base + bi * 128;
@@ -309,6 +334,7 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
             for (int k = 0; k < ksteps; ++k) umma_ts(t_o, t_p + k * 8, dv + k * 128, idesc_o, k != 0);
           }
           umma_commit(&pv_done[bi]);
+          umma_commit(&kv_empty[j % KV_STAGES]);               // this tile is done with K_j / V_j
         }
         __syncwarp();
       };
@@ -317,23 +343,18 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
       for (int j = 0; j < 2 && j < nblk; ++j) {              // both buffers start out free
         mbar_wait(&kv_full[j % KV_STAGES], 0);
         tc_fence_after();
-        for (int x = 0; x < n_tiles; ++x) issue_s(x, j);
+        issue_s(j);
       }
       for (int j = 0; j < nblk; ++j) {
         const uint32_t par = (j >> 1) & 1;
-        for (int x = 0; x < n_tiles; ++x) {
-          mbar_wait(&p_full[x * 2 + (j & 1)], par);          // P_x(j) written
-          tc_fence_after();
-          issue_pv(x, j);
-        }
-        if (leader) umma_commit(&kv_empty[j % KV_STAGES]);   // K_j / V_j consumed by both tiles
+        mbar_wait(&p_full[x * 2 + (j & 1)], par);            // P_x(j) written
+        tc_fence_after();
+        issue_pv(j);
         if (j + 2 < nblk) {
           mbar_wait(&kv_full[(j + 2) % KV_STAGES], ((j + 2) / KV_STAGES) & 1);
-          for (int x = 0; x < n_tiles; ++x) {
-            mbar_wait(&buf_free[x * 2 + (j & 1)], par);      // O_blk(j) folded: buffer j & 1 reusable
-            tc_fence_after();
-            issue_s(x, j + 2);
-          }
+          mbar_wait(&buf_free[x * 2 + (j & 1)], par);        // O_blk(j) folded: buffer j & 1 reusable
+          tc_fence_after();
+          issue_s(j + 2);
         }
       }
     }
@@ -360,8 +381,13 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
         uint64_t* pvd = &pv_done[x * 2 + (bf ^ 1)];
         uint64_t* bfr = &buf_free[x * 2 + (bf ^ 1)];
         const uint32_t pv_par = ((j - 1) >> 1) & 1;
+#if defined(VB200_ATTN_NOSOFTMAX)   // timing experiment: barrier traffic only
+        if (j > 0) { mbar_wait(pvd, pv_par); tc_fence_after(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bfr); }
+        l = 1.f;
+#else
         if (!tail) softmax_block<false>(t_buf, t_prev, pvd, pv_par, bfr, lane, j, 4, BKV, scale_log2, m, l, alpha_prev, o);
         else softmax_block<true>(t_buf, t_prev, pvd, pv_par, bfr, lane, j, n_chunks, last_valid, scale_log2, m, l, alpha_prev, o);
+#endif
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
