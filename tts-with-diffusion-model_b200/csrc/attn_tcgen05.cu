@@ -87,7 +87,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 
 // exp2 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + r with the 1.5 * 2^23
-// magic constant, 2^r by a cubic on [-0.5, 0.5] (|rel err| < 1.2e-4, far below the bf16 rounding
+// magic constant, 2^r by a cubic on [-0.5, 0.5] (|rel err| < 7.5e-5, far below the bf16 rounding
 // of P), exponent patched in with an integer add.  MUFU.EX2 runs at 16 lanes / clk / SM on B200
 // (tools/mufu_bench.cu), which makes a 128x128 softmax block MUFU-bound at about twice the time of
 // its MMAs; moving a share of the exponentials here rebalances the two pipes (the FA4 trick).
@@ -95,13 +95,13 @@ __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -126.0f);
   const float t = x + 12582912.0f;
   const float r = x - (t - 12582912.0f);
-  float p = fmaf(r, 0.05550357f, 0.24022650f);
-  p = fmaf(r, p, 0.69314720f);
-  p = fmaf(r, p, 1.0f);
+  float p = fmaf(r, 0.05517167f, 0.24261113f);     // minimax cubic of 2^r on [-0.5, 0.5]
+  p = fmaf(r, p, 0.69326097f);
+  p = fmaf(r, p, 0.99992806f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 #ifndef VB200_ATTN_EMU_PER_4
-#define VB200_ATTN_EMU_PER_4 0      // exponentials out of every 4 evaluated by ex2_poly instead of MUFU
+#define VB200_ATTN_EMU_PER_4 1      // exponentials out of every 4 evaluated by ex2_poly instead of MUFU
 #endif
 
 // 32 scores -> 32 probabilities (bf16, 16 TMEM columns); row sum tracked on 4 chains.
