@@ -301,9 +301,13 @@ def run_ours(args, wl):
     gemm_tf = g[0] / (g[1] * 1e-3) / 1e12
     attn_tf = at[0] / (at[1] * 1e-3) / 1e12
     step_total_ms = ms / (timesteps - 1)
+    traffic = None      # dram bytes per launch of the dominant GEMM from one committed `ncu --set full` capture
+    tf = ROOT / "profiles" / "r1_gemm_traffic.json"
+    if tf.exists():
+        traffic = json.loads(tf.read_text())
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (QKV/out/FFN1/FFN2/head launches)",
                 "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
-                "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": None,
+                "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
                 "avg_launch_ms": g[1] / g[2], "launches_timed": g[2],
                 "share_of_denoise_step": (g[1] / prof_steps) / step_total_ms,
                 "attention": {"kernel": "flash_attn_kernel", "achieved": attn_tf, "unit": "TFLOP/s",

@@ -233,3 +233,44 @@ def test_layernorm_variant_and_nar_level_loop():
     assert all(int(o.min()) >= 0 and int(o.max()) < K for o in out)
     with pytest.raises(ValueError):
         nar([x.to(DEV) for x in text], [x.to(DEV) for x in proms], [resps[0][:, :1].to(DEV), resps[1][:, :2].to(DEV)])
+
+
+def test_long_and_degenerate_utterances_tcgen05_vs_cuda_core_path():
+    """30 s utterance (T = 2 527, the C4 shape) next to degenerate ones (1 phone / 1 prompt frame /
+    1 response frame): tcgen05 path against the independent CUDA-core path, same packed layout."""
+    from vall_e.b200.engine import BatchLayout, DenoiserEngine
+    K, d, h, nl, S = 64, 128, 2, 2, 10
+    m, _ = _make(K, d, h, nl, S, "absorbing", seed=5)
+    lens = [(50, 225, 2250), (1, 1, 1), (2, 3, 255), (7, 120, 128)]
+    text, proms, xt = _batch(K, lens, 17)
+    t = torch.tensor([9, 0, 3, 5])
+    eng = m.engine()
+    lay = BatchLayout(text, proms, [len(x) for x in xt], DEV)
+    assert lay.max_T == 2527 and lay.M == 2527 + 5 + 262 + 257
+    resp = torch.cat(xt).to(DEV, torch.int32)
+    ws = eng.workspace(lay, logits_dtype=torch.float32)
+    a = eng.forward(lay, ws, resp, t.to(DEV, torch.int32), use_time=True).clone()
+    simt = DenoiserEngine(eng.w, simt=True)
+    ws2 = simt.workspace(lay, logits_dtype=torch.float32)
+    b = simt.forward(lay, ws2, resp, t.to(DEV, torch.int32), use_time=True)
+    assert torch.isfinite(a).all()
+    assert (a - b).abs().max().item() < 3e-2
+
+
+def test_generate_uniform_transition_graph_and_empty_edge_cases():
+    from vall_e.b200 import lib as L
+    K, d, h, nl, S = 64, 64, 1, 1, 6
+    m, _ = _make(K, d, h, nl, S, "uniform", seed=8)
+    g = torch.Generator().manual_seed(2)
+    text = [torch.randint(1, K, (3,), generator=g).to(DEV)]
+    proms = [torch.randint(0, K, (5, 8), generator=g).to(DEV)]
+    a = m.generate_audio(text, proms, resp_lens=[33], seed=1)
+    b = m.generate_audio(text, proms, resp_lens=[33], seed=1, use_graph=False)
+    assert torch.equal(a[0], b[0]) and a[0].shape == (33, 8)
+    with pytest.raises(ValueError):
+        m.generate_audio([], [], resp_lens=[])
+    # zero-row launches are accepted and do nothing
+    e = torch.empty(0, 64, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(64, 64, dtype=torch.bfloat16, device=DEV)
+    L.gemm_bf16(torch.empty(0, 64, dtype=torch.float32, device=DEV), e, w)
+    L.gather_rows_bf16(e, torch.empty(0, 64, device=DEV), torch.empty(0, dtype=torch.int32, device=DEV))
