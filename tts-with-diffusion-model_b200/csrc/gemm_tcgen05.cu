@@ -11,6 +11,8 @@
 // Output never leaves the SM through per-thread stores: each epilogue warp writes 32 rows x 128 B
 // into its own SWIZZLE_128B staging tile and one lane hands it to the TMA engine, which clips the
 // M / N tails and, for BIAS_RESIDUAL, performs out += tile at L2 (no read of the residual by SMs).
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -18,15 +20,24 @@
 namespace vb200 {
 
 namespace gemm {
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
-constexpr int B_BYTES = BN * BK * 2;            // 32 KB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;  // 48 KB
+// CTAS = 1: one CTA per 128x256 tile, stage = A 16 KB + W 32 KB, 4 stages.
+// CTAS = 2: a CTA pair (cluster of 2, cta_group::2) per 256x256 tile; each CTA stages its own 128
+//           rows of A and HALF of the W tile (128 rows), 32 KB per stage, 6 stages.  The pair's
+//           tensor cores read both halves, which halves every SM's shared-memory operand traffic —
+//           measured necessary: a lone CTA sustains 163 cycles per 128x256x16 MMA against 128 nominal.
+template <int CTAS> struct Cfg {
+  static constexpr int B_ROWS = BN / CTAS;
+  static constexpr int B_BYTES = B_ROWS * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = CTAS == 1 ? 4 : 6;
+};
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;   // 320
 constexpr int EPI_TILE_BYTES = 32 * 128;        // 32 rows x 128 B per epilogue warp
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_TILE_BYTES + 1024 /*align slack*/ +
-                           256 /*barriers*/;
+constexpr int SMEM_BYTES = 4 * 48 * 1024 + EPI_WARPS * EPI_TILE_BYTES + 1024 /*align slack*/ +
+                           256 /*barriers*/;     // 4 x 48 KB == 6 x 32 KB
 constexpr uint32_t TMEM_COLS = 512;
 }  // namespace gemm
 
@@ -47,11 +58,13 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaxf(x, 0.0f) - fabsf(r);
 }
 
-template <int EPI, typename OutT>
+template <int EPI, typename OutT, int CTAS>
 __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
     const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N, int K) {
   using namespace gemm;
+  constexpr int STAGES = Cfg<CTAS>::STAGES, STAGE_BYTES = Cfg<CTAS>::STAGE_BYTES, B_ROWS = Cfg<CTAS>::B_ROWS;
+  const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0;       // 0 = leader of the pair
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t pad = ((raw_addr + 1023u) & ~1023u) - raw_addr;
@@ -66,24 +79,26 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
+  // a "tile" is BM * CTAS rows; the CTAs of a pair take consecutive 128-row halves of it
+  const int num_m = (M + BM * CTAS - 1) / (BM * CTAS), num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_kb = (K + BK - 1) / BK;
+  const int tile0 = blockIdx.x / CTAS, tile_stride = gridDim.x / CTAS;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     tma_prefetch_desc(&tm_out);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * CTAS); }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (CTAS == 2) { tmem_alloc_pair(tmem_slot, TMEM_COLS); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -95,15 +110,23 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
       // ------------------------------------------------------------ TMA producer
       const bool leader = elect_one();
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
+        const int m_row = (m_blk * CTAS + cta_rank) * BM, n_row = n_blk * BN + cta_rank * B_ROWS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           if (leader) {
-            mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-            tma_load_2d(sa, &tm_a, &full[stage], kb * BK, m_blk * BM);
-            tma_load_2d(sa + A_BYTES, &tm_b, &full[stage], kb * BK, n_blk * BN);
+            if (CTAS == 2) {
+              // both CTAs' bytes are counted on the leader CTA's barrier
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * STAGE_BYTES);
+              tma_load_2d_pair(sa, &tm_a, &full[stage], kb * BK, m_row);
+              tma_load_2d_pair(sa + A_BYTES, &tm_b, &full[stage], kb * BK, n_row);
+            } else {
+              mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+              tma_load_2d(sa, &tm_a, &full[stage], kb * BK, m_row);
+              tma_load_2d(sa + A_BYTES, &tm_b, &full[stage], kb * BK, n_row);
+            }
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -111,13 +134,13 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
       }
     }
   } else if (warp == 1) {
-    {
-      // ------------------------------------------------------------ MMA issuer
+    if (cta_rank == 0) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA of a pair)
       const bool leader = elect_one();
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, false, false);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN, false, false);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&acc_empty[as], aphase ^ 1);
@@ -131,14 +154,19 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
           const uint64_t db = umma_desc_kmajor_sw128(sa + A_BYTES);
           if (leader) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)   // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
-              umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            umma_commit(&empty[stage]);         // frees the smem slot once these MMAs retire
+            for (int k = 0; k < BK / 16; ++k) { // +32 bytes (>>4 = 2) per UMMA_K inside the swizzle atom
+              if (CTAS == 2) umma_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+              else umma_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            }
+            if (CTAS == 2) umma_commit_pair(&empty[stage]);   // frees the slot in both CTAs
+            else umma_commit(&empty[stage]);    // frees the smem slot once these MMAs retire
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (leader) umma_commit(&acc_full[as]); // accumulator complete -> epilogue
+        if (leader) {                           // accumulator complete -> epilogue (of both CTAs)
+          if (CTAS == 2) umma_commit_pair(&acc_full[as]); else umma_commit(&acc_full[as]);
+        }
         __syncwarp();
       }
     }
@@ -155,13 +183,13 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     constexpr int CHUNKS = 128 / CHUNK_COLS;
     const bool epi_leader = elect_one();       // the lane that owns this warp's bulk-store group
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
-      const int row0 = m_blk * BM + quad * 32;
+      const int row0 = (m_blk * CTAS + cta_rank) * BM + quad * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * 128;
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
@@ -224,49 +252,85 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);     // one arrival per epilogue warp
+      if (lane == 0) {                                // one arrival per epilogue warp, on the leader's barrier
+        if (CTAS == 2 && cta_rank != 0) mbar_arrive_remote(&acc_empty[as], 0);
+        else mbar_arrive(&acc_empty[as]);
+      }
     }
     if (epi_leader) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // nobody leaves while the peer still uses it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTAS == 2) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
 // ---------------------------------------------------------------- host side
 template <int EPI, typename OutT>
-static int launch_gemm(void* out, vb200_dtype dt, const CUtensorMap& ta, const CUtensorMap& tb,
-                       const float* bias, int M, int N, int K, cudaStream_t st) {
+static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, const float* bias, int M, int N,
+                       int K, cudaStream_t st) {
   using namespace gemm;
-  auto kern = gemm_tcgen05_kernel<EPI, OutT>;
-  static bool configured = false;   // per template instantiation
-  if (!configured) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
+  // A/B knob: VB200_GEMM_CTAS=1 forces the single-CTA kernel
+  static int ctas = 0;
+  if (ctas == 0) {
+    const char* e = getenv("VB200_GEMM_CTAS");
+    ctas = (e && atoi(e) == 1) ? 1 : 2;
   }
-  CUtensorMap tout;   // store box: 32 rows x 128 bytes
-  const int esz = sizeof(OutT);
-  int rc = cached_tmap(&tout, dt, out, N, M, static_cast<uint64_t>(N) * esz, 128 / esz, 32);
+  CUtensorMap ta, tb, tout;
+  int rc = cached_tmap(&ta, VB200_BF16, A, K, M, static_cast<uint64_t>(K) * 2, BK, BM);
   if (rc != VB200_OK) return rc;
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, THREADS, SMEM_BYTES, st>>>(ta, tb, tout, bias, M, N, K);
+  rc = cached_tmap(&tb, VB200_BF16, W, K, N, static_cast<uint64_t>(K) * 2, BK, BN / ctas);
+  if (rc != VB200_OK) return rc;
+  const int esz = sizeof(OutT);   // store box: 32 rows x 128 bytes
+  rc = cached_tmap(&tout, dt, out, N, M, static_cast<uint64_t>(N) * esz, 128 / esz, 32);
+  if (rc != VB200_OK) return rc;
+  const int tiles = ((M + BM * ctas - 1) / (BM * ctas)) * ((N + BN - 1) / BN);
+  const int groups = num_sms() / ctas;
+  const int grid = (tiles < groups ? tiles : groups) * ctas;
+  if (ctas == 1) {
+    auto kern = gemm_tcgen05_kernel<EPI, OutT, 1>;
+    static bool configured = false;
+    if (!configured) {
+      VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      configured = true;
+    }
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(ta, tb, tout, bias, M, N, K);
+  } else {
+    auto kern = gemm_tcgen05_kernel<EPI, OutT, 2>;
+    static bool configured = false;
+    if (!configured) {
+      VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      configured = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, bias, M, N, K));
+  }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
 
 template <int EPI>
-static int launch_gemm_dtype(void* out, vb200_dtype dt, const CUtensorMap& ta, const CUtensorMap& tb,
-                             const float* bias, int M, int N, int K, cudaStream_t st) {
+static int launch_gemm_dtype(void* out, vb200_dtype dt, const void* A, const void* W, const float* bias, int M,
+                             int N, int K, cudaStream_t st) {
   switch (dt) {
-    case VB200_F32: return launch_gemm<EPI, float>(out, dt, ta, tb, bias, M, N, K, st);
-    case VB200_BF16: return launch_gemm<EPI, __nv_bfloat16>(out, dt, ta, tb, bias, M, N, K, st);
-    case VB200_F16: return launch_gemm<EPI, __half>(out, dt, ta, tb, bias, M, N, K, st);
+    case VB200_F32: return launch_gemm<EPI, float>(out, dt, A, W, bias, M, N, K, st);
+    case VB200_BF16: return launch_gemm<EPI, __nv_bfloat16>(out, dt, A, W, bias, M, N, K, st);
+    case VB200_F16: return launch_gemm<EPI, __half>(out, dt, A, W, bias, M, N, K, st);
   }
   set_error("gemm: unknown out dtype %d", static_cast<int>(dt));
   return VB200_ERR_INVALID;
@@ -288,22 +352,17 @@ extern "C" int vb200_gemm_bf16(void* out, vb200_dtype out_dtype, const void* A, 
   VB_REQUIRE(epi != VB200_EPI_BIAS_RESIDUAL || (residual && out_dtype == VB200_F32),
              "gemm: BIAS_RESIDUAL needs residual and fp32 output");
   if (M == 0) return VB200_OK;
-  CUtensorMap ta, tb;
-  int rc = cached_tmap(&ta, VB200_BF16, A, K, M, static_cast<uint64_t>(K) * 2, gemm::BK, gemm::BM);
-  if (rc != VB200_OK) return rc;
-  rc = cached_tmap(&tb, VB200_BF16, W, K, N, static_cast<uint64_t>(K) * 2, gemm::BK, gemm::BN);
-  if (rc != VB200_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epi) {
-    case VB200_EPI_NONE: return launch_gemm_dtype<VB200_EPI_NONE>(out, out_dtype, ta, tb, bias, M, N, K, st);
-    case VB200_EPI_BIAS: return launch_gemm_dtype<VB200_EPI_BIAS>(out, out_dtype, ta, tb, bias, M, N, K, st);
-    case VB200_EPI_BIAS_GELU: return launch_gemm_dtype<VB200_EPI_BIAS_GELU>(out, out_dtype, ta, tb, bias, M, N, K, st);
+    case VB200_EPI_NONE: return launch_gemm_dtype<VB200_EPI_NONE>(out, out_dtype, A, W, bias, M, N, K, st);
+    case VB200_EPI_BIAS: return launch_gemm_dtype<VB200_EPI_BIAS>(out, out_dtype, A, W, bias, M, N, K, st);
+    case VB200_EPI_BIAS_GELU: return launch_gemm_dtype<VB200_EPI_BIAS_GELU>(out, out_dtype, A, W, bias, M, N, K, st);
     case VB200_EPI_BIAS_RESIDUAL:
       // out (+)= acc + bias is a TMA reduce-add into `out`; a distinct residual is copied in first
       if (residual != static_cast<const float*>(out))
         VB_CHECK_CUDA(cudaMemcpyAsync(out, residual, static_cast<size_t>(M) * N * sizeof(float),
                                       cudaMemcpyDeviceToDevice, st));
-      return launch_gemm<VB200_EPI_BIAS_RESIDUAL, float>(out, out_dtype, ta, tb, bias, M, N, K, st);
+      return launch_gemm<VB200_EPI_BIAS_RESIDUAL, float>(out, out_dtype, A, W, bias, M, N, K, st);
   }
   set_error("gemm: unknown epilogue %d", static_cast<int>(epi));
   return VB200_ERR_INVALID;
