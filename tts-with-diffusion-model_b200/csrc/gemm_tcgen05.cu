@@ -42,20 +42,19 @@ constexpr uint32_t TMEM_COLS = 512;
 }  // namespace gemm
 
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)), erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7):
-  //   1 - erf(z) = t (a1 + t (a2 + t (a3 + t (a4 + t a5)))) exp(-z^2),  t = 1 / (1 + p z),  z = |x| / sqrt 2.
-  // With q = 0.5 (1 - erf(z)):  gelu(x) = x (1 - q) for x > 0 and x q for x < 0, i.e. relu(x) - |x q|.
-  // 16 instructions (2 MUFU): coefficients carry the 0.5, exp2 / rcp are the raw approx.ftz forms.
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float p = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
-  p = fmaf(t, p, 0.5f * 1.421413741f);
-  p = fmaf(t, p, 0.5f * -0.284496736f);
-  p = fmaf(t, p, 0.5f * 0.254829592f);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((z * -1.4426950408889634f) * z));
-  const float r = ((p * t) * e) * x;
-  return fmaxf(x, 0.0f) - fabsf(r);
+  // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) = relu(x) - |x| q(z),  q(z) = 0.5 erfc(z),  z = |x| / sqrt 2.
+  // log2 q(z) is smooth: a degree-6 minimax polynomial on [0, 6] gives |gelu error| < 4.5e-5 for all x
+  // (beyond z = 6, i.e. |x| > 8.5, q < 1e-17).  12 instructions, one MUFU (ex2).
+  const float z = fminf(fabsf(x) * 0.70710678118654752f, 6.0f);
+  float p = fmaf(z, 9.22344479e-05f, -2.20238999e-03f);
+  p = fmaf(z, p, 2.23510694e-02f);
+  p = fmaf(z, p, -1.29628107e-01f);
+  p = fmaf(z, p, -9.38564420e-01f);
+  p = fmaf(z, p, -1.62045550e+00f);
+  p = fmaf(z, p, -1.00044155e+00f);
+  float q;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(p));
+  return fmaxf(x, 0.0f) - fabsf(x * q);
 }
 
 template <int EPI, typename OutT, int CTAS>
@@ -274,11 +273,19 @@ template <int EPI, typename OutT>
 static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, const float* bias, int M, int N,
                        int K, cudaStream_t st) {
   using namespace gemm;
-  // A/B knob: VB200_GEMM_CTAS=1 forces the single-CTA kernel
-  static int ctas = 0;
-  if (ctas == 0) {
+  // CTA pairs are faster per MMA (~135 vs 163 cycles) but halve the number of schedulable tiles;
+  // pick by estimated waves x cycles.  VB200_GEMM_CTAS=1|2 forces one kernel (A/B measurements).
+  static int forced = -1;
+  if (forced < 0) {
     const char* e = getenv("VB200_GEMM_CTAS");
-    ctas = (e && atoi(e) == 1) ? 1 : 2;
+    forced = e ? atoi(e) : 0;
+  }
+  int ctas = forced;
+  if (ctas != 1 && ctas != 2) {
+    const int nn = (N + BN - 1) / BN, sms = num_sms();
+    const long t1 = static_cast<long>(((M + BM - 1) / BM) * nn + sms - 1) / sms * 163;
+    const long t2 = static_cast<long>(((M + 2 * BM - 1) / (2 * BM)) * nn + sms / 2 - 1) / (sms / 2) * 135;
+    ctas = t2 <= t1 ? 2 : 1;
   }
   CUtensorMap ta, tb, tout;
   int rc = cached_tmap(&ta, VB200_BF16, A, K, M, static_cast<uint64_t>(K) * 2, BK, BM);
