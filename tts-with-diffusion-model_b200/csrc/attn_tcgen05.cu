@@ -432,6 +432,7 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
                                        int32_t B, int32_t max_T, int32_t M, int32_t n_heads,
                                        float scale, vb200_stream_t stream) {
   using namespace attn;
+  if (M == 0) return VB200_OK;
   VB_REQUIRE(out_bf16 && qkv_bf16 && cu_rows, "flash_attn: null pointer");
   VB_REQUIRE(B >= 1 && B <= 65535 && n_heads >= 1 && n_heads <= 65535 && max_T >= 1 && M >= 0,
              "flash_attn: bad sizes B=%d heads=%d max_T=%d M=%d", B, n_heads, max_T, M);

@@ -554,6 +554,7 @@ extern "C" int vb200_q_sample(int32_t* x_out, const int32_t* x0, const int32_t* 
                               const int32_t* mask, const float* uniforms, const float* table,
                               int32_t n_tok, int32_t K, int32_t S, vb200_transition tr,
                               vb200_stream_t stream) {
+  if (n_tok == 0) return VB200_OK;
   VB_REQUIRE(x_out && x0 && t_tok && uniforms && table, "q_sample: null pointer");
   VB_REQUIRE(n_tok >= 0 && K >= 2 && S >= 1, "q_sample: bad sizes n_tok=%d K=%d S=%d", n_tok, K, S);
   if (n_tok == 0) return VB200_OK;
@@ -573,6 +574,7 @@ extern "C" int vb200_posterior_sample_from_logits(
     const int32_t* utt, const float* table, int32_t n_rows, int32_t n_levels, int32_t K,
     int32_t S, vb200_transition tr, vb200_noise noise, const float* uniforms, uint64_t seed,
     vb200_stream_t stream) {
+  if (n_rows == 0) return VB200_OK;
   VB_REQUIRE(x_out && logits && x_t && row_utt && t_utt && table, "posterior: null pointer");
   VB_REQUIRE(n_rows >= 0 && n_levels >= 1 && K >= 2 && S >= 1, "posterior: bad sizes");
   VB_REQUIRE(ld_logits >= static_cast<int64_t>(n_levels) * K, "posterior: ld_logits too small");

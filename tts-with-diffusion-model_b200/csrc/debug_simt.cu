@@ -96,6 +96,7 @@ using namespace vb200;
 extern "C" int vb200_gemm_bf16_simt(void* out, vb200_dtype out_dtype, const void* A, const void* W,
                                     const float* bias, const float* residual, int32_t M, int32_t N,
                                     int32_t K, vb200_epilogue epi, vb200_stream_t stream) {
+  if (M <= 0 || N <= 0) return VB200_OK;
   VB_REQUIRE(out && A && W, "gemm_simt: null pointer");
   VB_REQUIRE(epi == VB200_EPI_NONE || bias, "gemm_simt: epilogue %d needs bias", static_cast<int>(epi));
   VB_REQUIRE(epi != VB200_EPI_BIAS_RESIDUAL || (residual && out_dtype == VB200_F32),
@@ -119,6 +120,7 @@ extern "C" int vb200_attn_varlen_simt(void* out_bf16, const void* qkv_bf16, cons
                                       int32_t B, int32_t max_T, int32_t M, int32_t n_heads,
                                       float scale, vb200_stream_t stream) {
   (void)max_T;
+  if (M <= 0) return VB200_OK;
   VB_REQUIRE(out_bf16 && qkv_bf16 && cu_rows, "attn_simt: null pointer");
   VB_REQUIRE(B >= 1 && n_heads >= 1, "attn_simt: bad sizes");
   if (M <= 0) return VB200_OK;

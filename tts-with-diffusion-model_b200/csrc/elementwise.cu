@@ -252,6 +252,7 @@ extern "C" int vb200_embed_gather(float* x_out, const void* text_w, const void* 
                                   const int32_t* utt, const int32_t* row_utt,
                                   const int32_t* t_utt, int32_t M, int32_t d, int32_t K,
                                   int32_t resp_levels_in, vb200_stream_t stream) {
+  if (M <= 0) return VB200_OK;
   VB_REQUIRE(x_out && text_w && prom_w && resp_w && sep && pe && utt && row_utt,
              "embed_gather: null pointer");
   VB_REQUIRE(!time_w || t_utt, "embed_gather: time_w given without t_utt");
@@ -270,6 +271,7 @@ extern "C" int vb200_embed_gather(float* x_out, const void* text_w, const void* 
 extern "C" int vb200_adaln(void* out_bf16, const float* x, const float* table,
                            const int32_t* level_utt, const int32_t* row_utt, int32_t M, int32_t d,
                            float eps, float k, float c, vb200_stream_t stream) {
+  if (M <= 0) return VB200_OK;
   VB_REQUIRE(out_bf16 && x && table && level_utt && row_utt, "adaln: null pointer");
   VB_REQUIRE(d > 0 && d % 8 == 0 && d <= 2048, "adaln: d=%d must be a multiple of 8, <= 2048", d);
   if (M <= 0) return VB200_OK;
@@ -298,6 +300,7 @@ extern "C" int vb200_adaln(void* out_bf16, const float* x, const float* table,
 extern "C" int vb200_layernorm(void* out_bf16, const float* x, const float* weight,
                                const float* bias, int32_t M, int32_t d, float eps,
                                vb200_stream_t stream) {
+  if (M <= 0) return VB200_OK;
   VB_REQUIRE(out_bf16 && x && weight && bias, "layernorm: null pointer");
   VB_REQUIRE(d > 0 && d % 8 == 0 && d <= 2048, "layernorm: d=%d must be a multiple of 8, <= 2048", d);
   if (M <= 0) return VB200_OK;
@@ -309,6 +312,7 @@ extern "C" int vb200_layernorm(void* out_bf16, const float* x, const float* weig
 
 extern "C" int vb200_gather_rows_bf16(void* out_bf16, const float* x, const int32_t* row_index,
                                       int32_t n_rows, int32_t d, vb200_stream_t stream) {
+  if (n_rows <= 0) return VB200_OK;
   VB_REQUIRE(out_bf16 && x && row_index, "gather_rows: null pointer");
   VB_REQUIRE(d > 0 && d % 8 == 0, "gather_rows: d=%d must be a multiple of 8", d);
   if (n_rows <= 0) return VB200_OK;

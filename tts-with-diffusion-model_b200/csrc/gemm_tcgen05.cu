@@ -350,15 +350,15 @@ using namespace vb200;
 extern "C" int vb200_gemm_bf16(void* out, vb200_dtype out_dtype, const void* A, const void* W,
                                const float* bias, const float* residual, int32_t M, int32_t N,
                                int32_t K, vb200_epilogue epi, vb200_stream_t stream) {
-  VB_REQUIRE(out && A && W, "gemm: null pointer");
   VB_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad sizes M=%d N=%d K=%d", M, N, K);
+  if (M == 0) return VB200_OK;                    // nothing to do (empty tensors carry null pointers)
+  VB_REQUIRE(out && A && W, "gemm: null pointer");
   VB_REQUIRE(K % 8 == 0, "gemm: K=%d must be a multiple of 8 (TMA row stride is 16-byte granular)", K);
   VB_REQUIRE(N % 8 == 0, "gemm: N=%d must be a multiple of 8 (16-byte vector stores)", N);
   VB_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "gemm: out must be 16-byte aligned");
   VB_REQUIRE(epi == VB200_EPI_NONE || bias, "gemm: epilogue %d needs bias", static_cast<int>(epi));
   VB_REQUIRE(epi != VB200_EPI_BIAS_RESIDUAL || (residual && out_dtype == VB200_F32),
              "gemm: BIAS_RESIDUAL needs residual and fp32 output");
-  if (M == 0) return VB200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epi) {
     case VB200_EPI_NONE: return launch_gemm_dtype<VB200_EPI_NONE>(out, out_dtype, A, W, bias, M, N, K, st);
