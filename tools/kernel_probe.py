@@ -33,6 +33,14 @@ elif what == "gemm":
     b2 = torch.randn(1024, device=dev)
     for _ in range(3):
         L.gemm_bf16(x, out, W2, b2, x, L.EPI_BIAS_RESIDUAL)
+elif what == "gemm_big":     # FFN1 at the bench shape (256 utterances x 1027 rows)
+    M = 262912
+    A = torch.randn(M, 1024, device=dev).bfloat16()
+    W = torch.randn(4096, 1024, device=dev).bfloat16()
+    bias = torch.randn(4096, device=dev)
+    out = torch.empty(M, 4096, dtype=torch.bfloat16, device=dev)
+    for _ in range(3):
+        L.gemm_bf16(out, A, W, bias, None, L.EPI_BIAS_GELU)
 elif what == "posterior":
     sys.path.insert(0, str(ROOT / "tts-with-diffusion-model_b200"))
     from vall_e.vall_e import d3pm
