@@ -304,10 +304,12 @@ def run_ours(args, wl):
     traffic = None      # dram bytes per launch of the dominant GEMM from one committed `ncu --set full` capture
     tf = ROOT / "profiles" / "r1_gemm_traffic.json"
     if tf.exists():
-        traffic = json.loads(tf.read_text())
+        tj = json.loads(tf.read_text())
+        traffic = tj.get("bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (QKV/out/FFN1/FFN2/head launches)",
                 "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
                 "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
+                "traffic_note": "dram bytes of one FFN1 launch (largest GEMM) from profiles/r1_gemm_traffic.json; algorithmic 2.70 GB",
                 "avg_launch_ms": g[1] / g[2], "launches_timed": g[2],
                 "share_of_denoise_step": (g[1] / prof_steps) / step_total_ms,
                 "attention": {"kernel": "flash_attn_kernel", "achieved": attn_tf, "unit": "TFLOP/s",

@@ -373,19 +373,30 @@ __global__ void __launch_bounds__(256, 3) posterior_fast_kernel(
     const int x_t = nxt_xt;
     const float l_x = nxt_lx, l_m = nxt_lm;
     if (tok + stride < n_tok) prefetch(tok + stride);
-    // argmax of the logits (lowest index wins ties) and row max
+    // Row max; the arg max (lowest index wins ties) is only needed for greedy decoding and for
+    // t == 0 (raw logits, no noise, ar_discrete.py:407,413), so the sampling path pays for a plain max.
     Best top{-INFINITY, 0x7fffffff};
+    if (NOISE == VB200_NOISE_GREEDY || t == 0) {
 #pragma unroll
-    for (int r = 0; r < NR; ++r) {
-      const int j = (r >> 3) * 256 + lane * 8 + (r & 7);
-      if (v[r] > top.v) { top.v = v[r]; top.j = j; }     // ascending j inside a lane
+      for (int r = 0; r < NR; ++r) {
+        const int j = (r >> 3) * 256 + lane * 8 + (r & 7);
+        if (v[r] > top.v) { top.v = v[r]; top.j = j; }   // ascending j inside a lane
+      }
+      top = warp_best(top);
+    } else {
+      float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+#pragma unroll
+      for (int r = 4; r < NR; r += 4) {
+        m0 = fmaxf(m0, v[r]); m1 = fmaxf(m1, v[r + 1]); m2 = fmaxf(m2, v[r + 2]); m3 = fmaxf(m3, v[r + 3]);
+      }
+      top.v = warp_max(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
     }
-    top = warp_best(top);
     const float mx = top.v;
-    if (t == 0) {                                         // raw logits, no noise (ar_discrete.py:407,413)
+    if (t == 0) {
       if (lane == 0) x_out[tok] = top.j;
       continue;
     }
+    const float mx_l2 = -mx * kLog2e;
     float part[KC];                                       // per-lane partial sums of e_j, one per 8-chunk
     float lane_sum = 0.f;
 #pragma unroll
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(256, 3) posterior_fast_kernel(
       float acc = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float e = exp2f_fast((v[c * 8 + i] - mx) * kLog2e);
+        const float e = exp2f_fast(fmaf(v[c * 8 + i], kLog2e, mx_l2));
         v[c * 8 + i] = e;
         acc += e;
       }
@@ -424,20 +435,20 @@ __global__ void __launch_bounds__(256, 3) posterior_fast_kernel(
     const float coef = (a_gen - c_gen) * invZ * f1_oth;
     const float cst = (c_gen + kEps) * f1_oth;
     // special classes: true weight minus what the generic formula assigns them (>= 0)
-    const float e_x = exp2f_fast((l_x - mx) * kLog2e);
+    const float e_x = exp2f_fast(fmaf(l_x, kLog2e, mx_l2));
     const float ax = at_m ? a_m : a_gen, cx = at_m ? c_m : c_gen;
     const float w_x = f1_self * (fmaf(e_x * invZ, ax - cx, cx) + kEps);
     const float dx = fmaxf(w_x - fmaf(e_x, coef, cst), 0.f);
     float w_m = 0.f, dm = 0.f;
     if (absorbing && !at_m) {
-      const float e_m = exp2f_fast((l_m - mx) * kLog2e);
+      const float e_m = exp2f_fast(fmaf(l_m, kLog2e, mx_l2));
       w_m = f1_oth * (fmaf(e_m * invZ, a_m - c_m, c_m) + kEps);
       dm = fmaxf(w_m - fmaf(e_m, coef, cst), 0.f);
     }
     int pick;
     if (NOISE == VB200_NOISE_GREEDY) {
       // generic weights are monotone in the logit, special classes only gain: compare three candidates
-      float best_w = fmaf(exp2f_fast((top.v - mx) * kLog2e), coef, cst);
+      float best_w = fmaf(exp2f_fast(fmaf(top.v, kLog2e, mx_l2)), coef, cst);
       pick = top.j;
       if (top.j == x_t) best_w = w_x;
       else if (top.j == m) best_w = w_m;
