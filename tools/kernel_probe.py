@@ -12,8 +12,8 @@ L.load()
 dev = "cuda"
 what = sys.argv[1] if len(sys.argv) > 1 else "attn"
 torch.manual_seed(0)
-if what == "attn":
-    lens, heads = [2527] * 8, 16
+if what in ("attn", "attn_c3"):
+    lens, heads = ([2527] * 8, 16) if what == "attn" else ([1027] * 32, 16)
     M, d = sum(lens), heads * 64
     qkv = torch.randn(M, 3 * d, device=dev).bfloat16()
     cu = torch.tensor([0] + list(torch.tensor(lens).cumsum(0)), dtype=torch.int32, device=dev)

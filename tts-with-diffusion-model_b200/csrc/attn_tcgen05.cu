@@ -100,27 +100,67 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(r, p, 0.99992806f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
-#ifndef VB200_ATTN_EMU_PER_4
-#define VB200_ATTN_EMU_PER_4 1      // exponentials out of every 4 evaluated by ex2_poly instead of MUFU
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot per two lanes' worth of fp32 work.  The
+// exp pass is co-limited by instruction issue and MUFU.EX2, so halving the FMA-pipe instruction
+// count is what lets a larger share of the exponentials move off MUFU (tools/fma2_bench.cu).
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// two exponentials at once on the FMA / ALU pipes (same cubic as ex2_poly)
+__device__ __forceinline__ void ex2_poly2(uint64_t x, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  x = pack2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+  const uint64_t t = fadd2(x, pack2(12582912.0f, 12582912.0f));
+  const uint64_t u = fadd2(t, pack2(-12582912.0f, -12582912.0f));
+  const uint64_t r = ffma2(u, pack2(-1.0f, -1.0f), x);
+  uint64_t p = ffma2(r, pack2(0.05517167f, 0.05517167f), pack2(0.24261113f, 0.24261113f));
+  p = ffma2(r, p, pack2(0.69326097f, 0.69326097f));
+  p = ffma2(r, p, pack2(0.99992806f, 0.99992806f));
+  float t0, t1, q0, q1;
+  unpack2(t, t0, t1);
+  unpack2(p, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+#ifndef VB200_ATTN_EMU_PAIRS
+#define VB200_ATTN_EMU_PAIRS 6      // of the 16 score pairs of a chunk, how many take ex2_poly2 instead of MUFU
 #endif
 
-// 32 scores -> 32 probabilities (bf16, 16 TMEM columns); row sum tracked on 4 chains.
-__device__ __forceinline__ void exp_store_chunk(const uint32_t (&s)[32], uint32_t t_p_chunk, float scale_log2,
-                                                float mneg, float (&ps)[4]) {
+// 32 scores -> 32 probabilities (bf16, 16 TMEM columns); row sum tracked on two packed chains.
+__device__ __forceinline__ void exp_store_chunk(const uint32_t (&s)[32], uint32_t t_p_chunk, uint64_t scale2,
+                                                uint64_t mneg2, uint64_t (&ps)[2]) {
   uint32_t pk[16];
 #pragma unroll
-  for (int i = 0; i < 32; i += 4) {
-    const float x0 = fmaf(__uint_as_float(s[i]), scale_log2, mneg);
-    const float x1 = fmaf(__uint_as_float(s[i + 1]), scale_log2, mneg);
-    const float x2 = fmaf(__uint_as_float(s[i + 2]), scale_log2, mneg);
-    const float x3 = fmaf(__uint_as_float(s[i + 3]), scale_log2, mneg);
-    const float p0 = VB200_ATTN_EMU_PER_4 > 3 ? ex2_poly(x0) : ex2_approx(x0);
-    const float p1 = VB200_ATTN_EMU_PER_4 > 1 ? ex2_poly(x1) : ex2_approx(x1);
-    const float p2 = VB200_ATTN_EMU_PER_4 > 2 ? ex2_poly(x2) : ex2_approx(x2);
-    const float p3 = VB200_ATTN_EMU_PER_4 > 0 ? ex2_poly(x3) : ex2_approx(x3);
-    ps[0] += p0; ps[1] += p1; ps[2] += p2; ps[3] += p3;
-    pk[i >> 1] = pack_bf16x2(p0, p1);
-    pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+  for (int i = 0; i < 16; ++i) {
+    const uint64_t x = ffma2(pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), scale2, mneg2);
+    const bool emulate = ((i + 1) * VB200_ATTN_EMU_PAIRS) / 16 != (i * VB200_ATTN_EMU_PAIRS) / 16;
+    float p0, p1;
+    if (emulate) {
+      ex2_poly2(x, p0, p1);
+    } else {
+      float x0, x1;
+      unpack2(x, x0, x1);
+      p0 = ex2_approx(x0);
+      p1 = ex2_approx(x1);
+    }
+    ps[i & 1] = fadd2(ps[i & 1], pack2(p0, p1));
+    pk[i] = pack_bf16x2(p0, p1);
   }
   tmem_st_32x16(t_p_chunk, pk);
 }
@@ -145,14 +185,16 @@ __device__ __forceinline__ void max_chunk(uint32_t (&s)[32], int k_base, int las
 }
 
 // o = o * alpha + O_blk, O_blk read from TMEM columns [t_oblk, t_oblk + 64)
-__device__ __forceinline__ void fold_o_block(float (&o)[64], uint32_t t_oblk, float alpha) {
+__device__ __forceinline__ void fold_o_block(uint64_t (&o)[32], uint32_t t_oblk, float alpha) {
+  const uint64_t alpha2 = pack2(alpha, alpha);
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     uint32_t r[32];
     tmem_ld_32x32p(t_oblk + c * 32, r);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(r[i]));
+    for (int i = 0; i < 16; ++i)
+      o[c * 16 + i] = ffma2(o[c * 16 + i], alpha2, pack2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])));
   }
 }
 
@@ -162,7 +204,7 @@ template <bool TAIL>
 __device__ __forceinline__ void softmax_block(uint32_t t_buf, uint32_t t_prev, uint64_t* pv_done_prev,
                                               uint32_t pv_parity, uint64_t* buf_free_prev, int lane, int j,
                                               int n_chunks, int last_valid, float scale_log2, float& m,
-                                              float& l, float& alpha_prev, float (&o)[64]) {
+                                              float& l, float& alpha_prev, uint64_t (&o)[32]) {
   // pass 1: block max -> new running max, rescale factor of everything accumulated so far
   float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll 1
@@ -177,7 +219,8 @@ __device__ __forceinline__ void softmax_block(uint32_t t_buf, uint32_t t_prev, u
   const float alpha = ex2_approx((m - m_new) * scale_log2);   // 0 on the first block (m = -inf)
   m = m_new;
   const float mneg = -m_new * scale_log2;
-  float ps[4] = {0.f, 0.f, 0.f, 0.f};
+  const uint64_t scale2 = pack2(scale_log2, scale_log2), mneg2 = pack2(mneg, mneg);
+  uint64_t ps[2] = {0ull, 0ull};
   float unused[4] = {0.f, 0.f, 0.f, 0.f};
   // pass 2, first half
 #pragma unroll 1
@@ -187,7 +230,7 @@ __device__ __forceinline__ void softmax_block(uint32_t t_buf, uint32_t t_prev, u
     tmem_ld_32x32p(t_buf + c * 32, s);
     tmem_ld_wait();
     if (TAIL) max_chunk<true>(s, c * 32, last_valid, unused);     // re-apply the key mask
-    exp_store_chunk(s, t_buf + c * 16, scale_log2, mneg, ps);
+    exp_store_chunk(s, t_buf + c * 16, scale2, mneg2, ps);
   }
   // fold in O_blk(j-1) (its MMAs were issued a whole block ago) and hand its buffer back to the MMA warp
   if (j > 0) {
@@ -206,9 +249,12 @@ __device__ __forceinline__ void softmax_block(uint32_t t_buf, uint32_t t_prev, u
     tmem_ld_32x32p(t_buf + c * 32, s);
     tmem_ld_wait();
     if (TAIL) max_chunk<true>(s, c * 32, last_valid, unused);
-    exp_store_chunk(s, t_buf + c * 16, scale_log2, mneg, ps);
+    exp_store_chunk(s, t_buf + c * 16, scale2, mneg2, ps);
   }
-  l = fmaf(l, alpha, (ps[0] + ps[1]) + (ps[2] + ps[3]));
+  float s0, s1, s2, s3;
+  unpack2(ps[0], s0, s1);
+  unpack2(ps[1], s2, s3);
+  l = fmaf(l, alpha, (s0 + s1) + (s2 + s3));
   alpha_prev = alpha;
 }
 
@@ -367,9 +413,9 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
       const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
       const uint32_t t_x = tmem_base + lane_off + x * 256;      // this tile's two buffers
       float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-      float o[64];
+      uint64_t o[32];                                  // 64 fp32 accumulators as f32x2 pairs
 #pragma unroll
-      for (int i = 0; i < 64; ++i) o[i] = 0.f;
+      for (int i = 0; i < 32; ++i) o[i] = 0ull;
 
       for (int j = 0; j < nblk; ++j) {
         const bool tail = (j == nblk - 1) && last_valid < BKV;
@@ -403,13 +449,16 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
         const float inv = 1.0f / l;
         __nv_bfloat16* o_dst = out + static_cast<size_t>(row0 + q_row) * d + h * HD;
 #pragma unroll
-        for (int i = 0; i < 64; i += 8) {
+        for (int i = 0; i < 32; i += 4) {
+          float v[8];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) unpack2(o[i + k], v[2 * k], v[2 * k + 1]);
           uint4 pk;
-          pk.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv);
-          pk.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
-          pk.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv);
-          pk.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
-          *reinterpret_cast<uint4*>(o_dst + i) = pk;
+          pk.x = pack_bf16x2(v[0] * inv, v[1] * inv);
+          pk.y = pack_bf16x2(v[2] * inv, v[3] * inv);
+          pk.z = pack_bf16x2(v[4] * inv, v[5] * inv);
+          pk.w = pack_bf16x2(v[6] * inv, v[7] * inv);
+          *reinterpret_cast<uint4*>(o_dst + 2 * i) = pk;
         }
       }
     }
