@@ -1,25 +1,30 @@
 // Non-causal variable-length flash attention, head_dim 64 (reference
 // base.py:112-127 materialises (b, i, j, h) scores + mask + softmax in HBM).
 //
-// One CTA = (utterance, head, PAIR of 128-query tiles A/B); it walks the utterance's keys in
-// blocks of 128.  12 warps:
-//   warp 0 lane 0 : TMA producer  — Q_A, Q_B once, then K/V blocks through a 4-stage ring
-//   warps 1, 2    : MMA issuers of tile A / tile B (one elected lane each)
-//                                   S_X = Q_X K^T   (tcgen05.mma 128xNx16, SS, both K-major)
-//                                   O_blk = P_X V   (128x64x16, A = P_X from TMEM, B = V straight
+// One CTA = (utterance, head, one 128-query tile); it walks the utterance's keys in blocks of 128.
+// TWO CTAs share an SM (256 TMEM columns and ~81 KB of shared memory each), so one tile's
+// start-up, drain and barrier round trips are covered by the other tile's steady state, and the
+// nearly empty last tile of a ragged utterance only idles half an SM.  6 warps:
+//   warp 0        : TMA producer  — Q once, then K and V blocks through two 2-slot rings (K_j is
+//                   released as soon as S(j) has retired, V_j when O_blk(j) has)
+//   warp 1        : MMA issuer (one elected lane)
+//                                   S = Q K^T       (tcgen05.mma 128xNx16, SS, both K-major)
+//                                   O_blk = P V     (128x64x16, A = P from TMEM, B = V straight
 //                                                    from the TMA tile as an MN-major operand)
-//   warps 4..7    : softmax of tile A, warps 8..11: softmax of tile B — thread = one query row.
+//   warps 2..5    : softmax — thread = one query row.
 // Measured on B200 (profiles/): a softmax -> MMA -> softmax round trip (mbarrier hops + MMA
 // latency) costs ~900 cycles, more than the MMAs of a block, and with one score buffer per tile
-// that round trip sits on the critical path of every key block (removing the exponentials did not
-// change the kernel's time).  So every tile owns TWO 128-column TMEM buffers:
-//     buffer (j & 1) of tile X:  S_X(j) [128 cols]  ->  P_X(j) bf16 in cols 0..63 (written over the
-//     consumed scores)  ->  O_blk(j) = P_X(j) V_j fp32 in cols 64..127
-// S_X(j+1) is computed into the other buffer while block j is still being exponentiated, so a
+// that round trip sits on the critical path of every key block.  So the tile owns TWO 128-column
+// TMEM buffers:
+//     buffer (j & 1):  S(j) [128 cols]  ->  P(j) bf16 in cols 0..63 (written over the consumed
+//     scores)  ->  O_blk(j) = P(j) V_j fp32 in cols 64..127
+// S(j+1) is computed into the other buffer while block j is still being exponentiated, so a
 // softmax warp normally finds its next scores ready.  O is accumulated in registers (fp32, the
 // standard online-softmax recurrence o = o * alpha_j + O_blk(j)); block j-1's O_blk is folded in
-// halfway through block j's exp pass, which is also what frees that buffer for S_X(j+1).
-// TMEM (512 columns): A0 | A1 | B0 | B1.
+// halfway through block j's exp pass, which is also what frees that buffer for S(j+1).
+// The tensor pipe is not the limit: a block's 4 + 8 MMAs sustain ~570 cycles (tools/mma_bench.cu)
+// against ~1500 for the softmax of a 128x128 block, which is co-limited by instruction issue and
+// MUFU.EX2 — hence the packed f32x2 arithmetic and the polynomial exp2 below.
 // Keys past the utterance end are masked to -inf — the reference's key-padding mask
 // (base.py:119-124) in the packed-row layout — and the last key block only issues the MMAs
 // (N resp. K rounded up to 16) its valid keys need.
@@ -28,11 +33,11 @@
 namespace vb200 {
 
 namespace attn {
-constexpr int BQ = 128, BKV = 128, HD = 64, KV_STAGES = 4;
+constexpr int BQ = 128, BKV = 128, HD = 64, KV_STAGES = 2;
 constexpr int TILE_BYTES = 128 * HD * 2;  // 16 KB: 128 rows x 128 B
-constexpr uint32_t TMEM_COLS = 512;
-constexpr int THREADS = 12 * 32;          // control warpgroup + two softmax warpgroups
-constexpr int SMEM_BYTES = TILE_BYTES * (2 + 2 * KV_STAGES) + 1024 + 256;
+constexpr uint32_t TMEM_COLS = 256;         // two CTAs share an SM
+constexpr int THREADS = 6 * 32;           // TMA warp, MMA warp, four softmax warps
+constexpr int SMEM_BYTES = TILE_BYTES * (1 + 2 * KV_STAGES) + 1024 + 256;
 }  // namespace attn
 
 __device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -258,15 +263,14 @@ __device__ __forceinline__ void softmax_block(uint32_t t_buf, uint32_t t_prev, u
   alpha_prev = alpha;
 }
 
-__global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
+__global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
     const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
     const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2) {
   using namespace attn;
-  const int b = blockIdx.z, h = blockIdx.y, qp = blockIdx.x;
+  const int b = blockIdx.z, h = blockIdx.y, qt = blockIdx.x;
   const int row0 = cu_rows[b];
   const int T = cu_rows[b + 1] - row0;
-  if (qp * 2 * BQ >= T) return;                   // uniform early exit, before any allocation
-  const bool has_b = qp * 2 * BQ + BQ < T;        // second tile of the pair holds valid rows
+  if (qt * BQ >= T) return;                       // uniform early exit, before any allocation
   const int nblk = (T + BKV - 1) / BKV;
   const int last_valid = T - (nblk - 1) * BKV;    // keys inside the utterance in the last block
   const int last_n = (last_valid + 15) & ~15;     // MMA extent of the last block (multiple of 16)
@@ -275,18 +279,21 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* s_q = smem;                            // Q_A, Q_B
-  uint8_t* s_kv = smem + 2 * TILE_BYTES;          // stage s: K at s*2*TILE, V right after
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + 2 * KV_STAGES * TILE_BYTES);
+  uint8_t* s_q = smem;                            // Q tile
+  uint8_t* s_k = smem + TILE_BYTES;               // K ring [KV_STAGES]
+  uint8_t* s_v = s_k + KV_STAGES * TILE_BYTES;    // V ring [KV_STAGES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_v + KV_STAGES * TILE_BYTES);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;                   // [KV_STAGES]
-  uint64_t* kv_empty = kv_full + KV_STAGES;       // [KV_STAGES]
-  // per (tile x, buffer bf) at index x * 2 + bf; every one of them completes once per two blocks
-  uint64_t* s_full = kv_empty + KV_STAGES;        // [4]  scores of the block in this buffer complete
-  uint64_t* p_full = s_full + 4;                  // [4]  P written (one arrival per softmax warp)
-  uint64_t* pv_done = p_full + 4;                 // [4]  O_blk = P V retired
-  uint64_t* buf_free = pv_done + 4;               // [4]  O_blk folded into registers: buffer reusable
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_free + 4);
+  uint64_t* k_full = bars + 1;                    // [KV_STAGES]
+  uint64_t* k_empty = k_full + KV_STAGES;         // [KV_STAGES]  S(j) retired: K_j no longer needed
+  uint64_t* v_full = k_empty + KV_STAGES;         // [KV_STAGES]
+  uint64_t* v_empty = v_full + KV_STAGES;         // [KV_STAGES]  O_blk(j) retired: V_j no longer needed
+  // per TMEM buffer bf; every one of them completes once per two blocks
+  uint64_t* s_full = v_empty + KV_STAGES;         // [2]  scores of the block in this buffer complete
+  uint64_t* p_full = s_full + 2;                  // [2]  P written (one arrival per softmax warp)
+  uint64_t* pv_done = p_full + 2;                 // [2]  O_blk = P V retired
+  uint64_t* buf_free = pv_done + 2;               // [2]  O_blk folded into registers: buffer reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_free + 2);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
@@ -294,8 +301,10 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_qkv);
     mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], has_b ? 2 : 1); }
-    for (int i = 0; i < 4; ++i) {
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&buf_free[i], 4);
     }
     fence_barrier_init();
@@ -315,151 +324,146 @@ __global__ void __launch_bounds__(attn::THREADS, 1) flash_attn_kernel(
   // an elect / R2UR "waterfall" loop: measured 129 cycles per MMA regardless of shape instead of
   // 56-99 (tools/mma_bench.cu), which alone made this kernel tensor-issue bound.
   if (warp == 0) {
-    {
-      // ---------------------------------------------------------- TMA producer
-      const bool leader = elect_one();
+    // ------------------------------------------------------------ TMA producer
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_arrive_expect_tx(q_full, TILE_BYTES);
+      tma_load_2d(s_q, &tm_qkv, q_full, h * HD, row0 + qt * BQ);
+    }
+    for (int j = 0; j < nblk; ++j) {
+      const int s = j % KV_STAGES;
+      const uint32_t ph = (j / KV_STAGES) & 1;
+      mbar_wait(&k_empty[s], ph ^ 1);
       if (leader) {
-        mbar_arrive_expect_tx(q_full, (has_b ? 2 : 1) * TILE_BYTES);
-        tma_load_2d(s_q, &tm_qkv, q_full, h * HD, row0 + qp * 2 * BQ);
-        if (has_b) tma_load_2d(s_q + TILE_BYTES, &tm_qkv, q_full, h * HD, row0 + qp * 2 * BQ + BQ);
+        mbar_arrive_expect_tx(&k_full[s], TILE_BYTES);
+        tma_load_2d(s_k + s * TILE_BYTES, &tm_qkv, &k_full[s], d + h * HD, row0 + j * BKV);
       }
-      for (int j = 0; j < nblk; ++j) {
-        const int s = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        uint8_t* sk = s_kv + s * 2 * TILE_BYTES;
-        if (leader) {
-          mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-          tma_load_2d(sk, &tm_qkv, &kv_full[s], d + h * HD, row0 + j * BKV);
-          tma_load_2d(sk + TILE_BYTES, &tm_qkv, &kv_full[s], 2 * d + h * HD, row0 + j * BKV);
-        }
-        __syncwarp();
+      __syncwarp();
+      mbar_wait(&v_empty[s], ph ^ 1);
+      if (leader) {
+        mbar_arrive_expect_tx(&v_full[s], TILE_BYTES);
+        tma_load_2d(s_v + s * TILE_BYTES, &tm_qkv, &v_full[s], 2 * d + h * HD, row0 + j * BKV);
       }
+      __syncwarp();
     }
-  } else if (warp == 1 || warp == 2) {
-    // ------------------------------------------------------------ MMA issuers, one warp per tile
-    // Tile A and tile B are served by separate warps so that neither tile's MMAs ever wait on the
-    // other tile's softmax: the two softmax pipelines drift apart in phase and share the MUFU pipe
-    // instead of queueing on it in lockstep.  Everything needed per MMA is a 32-bit add on a
-    // precomputed descriptor (smem addresses are < 2^18, so the 14-bit start-address field of the
-    // low word never carries).
-    const int x = warp - 1;
-    if (x == 0 || has_b) {
-      const bool leader = elect_one();
-      const uint32_t idesc_o = umma_idesc_bf16(BQ, HD, false, true);        // B = V, MN-major
-      const uint32_t idesc_s_full = umma_idesc_bf16(BQ, BKV, false, false);
-      const uint32_t idesc_s_last = umma_idesc_bf16(BQ, last_n, false, false);
-      const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(s_q + x * TILE_BYTES));
-      const uint64_t dk_base = umma_desc_kmajor_sw128(smem_u32(s_kv));
-      const uint64_t dv_base = umma_desc_mnmajor_sw128(smem_u32(s_kv + TILE_BYTES), 1024);
-      constexpr uint32_t kTileStep = TILE_BYTES >> 4;          // descriptor units (16 B)
-      auto issue_s = [&](int j) {             // S_x(j) = Q_x K_j^T into buffer j & 1
-        const uint64_t dk = dk_base + static_cast<uint32_t>(j % KV_STAGES) * (2 * kTileStep);
-        const uint32_t idesc_s = (j == nblk - 1) ? idesc_s_last : idesc_s_full;
-        const int bi = x * 2 + (j & 1);
-        const uint32_t t_dst = tmem_base + bi * 128;
-        if (leader) {
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    // Everything needed per MMA is a 32-bit add on a precomputed descriptor (smem addresses are
+    // < 2^18, so the 14-bit start-address field of the low word never carries).
+    const bool leader = elect_one();
+    const uint32_t idesc_o = umma_idesc_bf16(BQ, HD, false, true);        // B = V, MN-major
+    const uint32_t idesc_s_full = umma_idesc_bf16(BQ, BKV, false, false);
+    const uint32_t idesc_s_last = umma_idesc_bf16(BQ, last_n, false, false);
+    const uint64_t dq = umma_desc_kmajor_sw128(smem_u32(s_q));
+    const uint64_t dk_base = umma_desc_kmajor_sw128(smem_u32(s_k));
+    const uint64_t dv_base = umma_desc_mnmajor_sw128(smem_u32(s_v), 1024);
+    constexpr uint32_t kTileStep = TILE_BYTES >> 4;          // descriptor units (16 B)
+    auto issue_s = [&](int j) {             // S(j) = Q K_j^T into buffer j & 1
+      const int st = j % KV_STAGES;
+      const uint64_t dk = dk_base + static_cast<uint32_t>(st) * kTileStep;
+      const uint32_t idesc_s = (j == nblk - 1) ? idesc_s_last : idesc_s_full;
+      const int bi = j & 1;
+      const uint32_t t_dst = tmem_base + bi * 128;
+      if (leader) {
 #pragma unroll
-          for (int k = 0; k < HD / 16; ++k) umma_ss(t_dst, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-          umma_commit(&s_full[bi]);
-        }
-        __syncwarp();
-      };
-      auto issue_pv = [&](int j) {            // O_blk(j) = P_x(j) V_j, inside buffer j & 1
-        const uint64_t dv = dv_base + static_cast<uint32_t>(j % KV_STAGES) * (2 * kTileStep);
-        const int bi = x * 2 + (j & 1);
-        const uint32_t t_p = tmem_base + bi * 128;
-        const uint32_t t_o = t_p + 64;
-        if (leader) {
-          if (j != nblk - 1) {
+        for (int k = 0; k < HD / 16; ++k) umma_ss(t_dst, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[bi]);
+        umma_commit(&k_empty[st]);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int j) {            // O_blk(j) = P(j) V_j, inside buffer j & 1
+      const int st = j % KV_STAGES;
+      const uint64_t dv = dv_base + static_cast<uint32_t>(st) * kTileStep;
+      const int bi = j & 1;
+      const uint32_t t_p = tmem_base + bi * 128;
+      const uint32_t t_o = t_p + 64;
+      if (leader) {
+        if (j != nblk - 1) {
 #pragma unroll
-            for (int k = 0; k < BKV / 16; ++k)                 // 16 key rows = 16 * 128 B = 128 units
-              umma_ts(t_o, t_p + k * 8, dv + k * 128, idesc_o, k != 0);
-          } else {
-            const int ksteps = last_n / 16;
-            for (int k = 0; k < ksteps; ++k) umma_ts(t_o, t_p + k * 8, dv + k * 128, idesc_o, k != 0);
-          }
-          umma_commit(&pv_done[bi]);
-          umma_commit(&kv_empty[j % KV_STAGES]);               // this tile is done with K_j / V_j
+          for (int k = 0; k < BKV / 16; ++k)                 // 16 key rows = 16 * 128 B = 128 units
+            umma_ts(t_o, t_p + k * 8, dv + k * 128, idesc_o, k != 0);
+        } else {
+          const int ksteps = last_n / 16;
+          for (int k = 0; k < ksteps; ++k) umma_ts(t_o, t_p + k * 8, dv + k * 128, idesc_o, k != 0);
         }
-        __syncwarp();
-      };
-      mbar_wait(q_full, 0);
+        umma_commit(&pv_done[bi]);
+        umma_commit(&v_empty[st]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    tc_fence_after();
+    for (int j = 0; j < 2 && j < nblk; ++j) {              // both buffers start out free
+      mbar_wait(&k_full[j % KV_STAGES], (j / KV_STAGES) & 1);
       tc_fence_after();
-      for (int j = 0; j < 2 && j < nblk; ++j) {              // both buffers start out free
-        mbar_wait(&kv_full[j % KV_STAGES], 0);
+      issue_s(j);
+    }
+    for (int j = 0; j < nblk; ++j) {
+      const uint32_t par = (j >> 1) & 1;
+      mbar_wait(&v_full[j % KV_STAGES], (j / KV_STAGES) & 1);
+      mbar_wait(&p_full[j & 1], par);                      // P(j) written
+      tc_fence_after();
+      issue_pv(j);
+      if (j + 2 < nblk) {
+        mbar_wait(&k_full[(j + 2) % KV_STAGES], ((j + 2) / KV_STAGES) & 1);
+        mbar_wait(&buf_free[j & 1], par);                  // O_blk(j) folded: buffer j & 1 reusable
         tc_fence_after();
-        issue_s(j);
-      }
-      for (int j = 0; j < nblk; ++j) {
-        const uint32_t par = (j >> 1) & 1;
-        mbar_wait(&p_full[x * 2 + (j & 1)], par);            // P_x(j) written
-        tc_fence_after();
-        issue_pv(j);
-        if (j + 2 < nblk) {
-          mbar_wait(&kv_full[(j + 2) % KV_STAGES], ((j + 2) / KV_STAGES) & 1);
-          mbar_wait(&buf_free[x * 2 + (j & 1)], par);        // O_blk(j) folded: buffer j & 1 reusable
-          tc_fence_after();
-          issue_s(j + 2);
-        }
+        issue_s(j + 2);
       }
     }
-  } else if (warp >= 4) {
-    // ============================================================== softmax / output warpgroups
-    const int x = (warp - 4) >> 2;                     // 0: tile A, 1: tile B
-    if (x == 0 || has_b) {
-      const int quad = warp & 3;
-      const int r_tile = quad * 32 + lane;             // query row inside the tile
-      const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
-      const uint32_t t_x = tmem_base + lane_off + x * 256;      // this tile's two buffers
-      float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-      uint64_t o[32];                                  // 64 fp32 accumulators as f32x2 pairs
+  } else {
+    // ============================================================== softmax / output warps 2..5
+    const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
+    const int r_tile = quad * 32 + lane;               // query row inside the tile
+    const uint32_t t_x = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+    uint64_t o[32];                                    // 64 fp32 accumulators as f32x2 pairs
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = 0ull;
+    for (int i = 0; i < 32; ++i) o[i] = 0ull;
 
-      for (int j = 0; j < nblk; ++j) {
-        const bool tail = (j == nblk - 1) && last_valid < BKV;
-        const int n_chunks = tail ? (last_n + 31) / 32 : 4;
-        const int bf = j & 1;
-        mbar_wait(&s_full[x * 2 + bf], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t t_buf = t_x + bf * 128, t_prev = t_x + (bf ^ 1) * 128;
-        uint64_t* pvd = &pv_done[x * 2 + (bf ^ 1)];
-        uint64_t* bfr = &buf_free[x * 2 + (bf ^ 1)];
-        const uint32_t pv_par = ((j - 1) >> 1) & 1;
-#if defined(VB200_ATTN_NOSOFTMAX)   // timing experiment: barrier traffic only
-        if (j > 0) { mbar_wait(pvd, pv_par); tc_fence_after(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bfr); }
-        l = 1.f;
-#else
-        if (!tail) softmax_block<false>(t_buf, t_prev, pvd, pv_par, bfr, lane, j, 4, BKV, scale_log2, m, l, alpha_prev, o);
-        else softmax_block<true>(t_buf, t_prev, pvd, pv_par, bfr, lane, j, n_chunks, last_valid, scale_log2, m, l, alpha_prev, o);
-#endif
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[x * 2 + bf]);  // one arrival per warp
-      }
-      // last block's O_blk, then O / l -> bf16 rows
-      const int jl = nblk - 1;
-      mbar_wait(&pv_done[x * 2 + (jl & 1)], (jl >> 1) & 1);
+    for (int j = 0; j < nblk; ++j) {
+      const bool tail = (j == nblk - 1) && last_valid < BKV;
+      const int n_chunks = tail ? (last_n + 31) / 32 : 4;
+      const int bf = j & 1;
+      mbar_wait(&s_full[bf], (j >> 1) & 1);
       tc_fence_after();
-      fold_o_block(o, t_x + (jl & 1) * 128 + 64, alpha_prev);
-      const int q_row = (qp * 2 + x) * BQ + r_tile;
-      if (q_row < T) {
-        const float inv = 1.0f / l;
-        __nv_bfloat16* o_dst = out + static_cast<size_t>(row0 + q_row) * d + h * HD;
+      const uint32_t t_buf = t_x + bf * 128, t_prev = t_x + (bf ^ 1) * 128;
+      uint64_t* pvd = &pv_done[bf ^ 1];
+      uint64_t* bfr = &buf_free[bf ^ 1];
+      const uint32_t pv_par = ((j - 1) >> 1) & 1;
+#if defined(VB200_ATTN_NOSOFTMAX)   // timing experiment: barrier traffic only
+      if (j > 0) { mbar_wait(pvd, pv_par); tc_fence_after(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bfr); }
+      l = 1.f; (void)n_chunks; (void)t_buf; (void)t_prev; (void)m;
+#else
+      if (!tail) softmax_block<false>(t_buf, t_prev, pvd, pv_par, bfr, lane, j, 4, BKV, scale_log2, m, l, alpha_prev, o);
+      else softmax_block<true>(t_buf, t_prev, pvd, pv_par, bfr, lane, j, n_chunks, last_valid, scale_log2, m, l, alpha_prev, o);
+#endif
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[bf]);         // one arrival per warp
+    }
+    // last block's O_blk, then O / l -> bf16 rows
+    const int jl = nblk - 1;
+    mbar_wait(&pv_done[jl & 1], (jl >> 1) & 1);
+    tc_fence_after();
+    fold_o_block(o, t_x + (jl & 1) * 128 + 64, alpha_prev);
+    const int q_row = qt * BQ + r_tile;
+    if (q_row < T) {
+      const float inv = 1.0f / l;
+      __nv_bfloat16* o_dst = out + static_cast<size_t>(row0 + q_row) * d + h * HD;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          float v[8];
+      for (int i = 0; i < 32; i += 4) {
+        float v[8];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) unpack2(o[i + k], v[2 * k], v[2 * k + 1]);
-          uint4 pk;
-          pk.x = pack_bf16x2(v[0] * inv, v[1] * inv);
-          pk.y = pack_bf16x2(v[2] * inv, v[3] * inv);
-          pk.z = pack_bf16x2(v[4] * inv, v[5] * inv);
-          pk.w = pack_bf16x2(v[6] * inv, v[7] * inv);
-          *reinterpret_cast<uint4*>(o_dst + 2 * i) = pk;
-        }
+        for (int k = 0; k < 4; ++k) unpack2(o[i + k], v[2 * k], v[2 * k + 1]);
+        uint4 pk;
+        pk.x = pack_bf16x2(v[0] * inv, v[1] * inv);
+        pk.y = pack_bf16x2(v[2] * inv, v[3] * inv);
+        pk.z = pack_bf16x2(v[4] * inv, v[5] * inv);
+        pk.w = pack_bf16x2(v[6] * inv, v[7] * inv);
+        *reinterpret_cast<uint4*>(o_dst + 2 * i) = pk;
       }
     }
   }
@@ -491,11 +495,13 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
   int rc = cached_tmap(&tm, VB200_BF16, qkv_bf16, static_cast<uint64_t>(3) * d, M,
                        static_cast<uint64_t>(3) * d * 2, HD, 128);
   if (rc != VB200_OK) return rc;
-  dim3 grid((max_T + 2 * BQ - 1) / (2 * BQ), n_heads, B);
+  dim3 grid((max_T + BQ - 1) / BQ, n_heads, B);
   const float sl2 = scale * 1.4426950408889634f;
   static bool configured = false;
   if (!configured) {
     VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));   // two CTAs per SM
     configured = true;
   }
   flash_attn_kernel<<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
