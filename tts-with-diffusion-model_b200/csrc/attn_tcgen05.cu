@@ -144,13 +144,12 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x, float& p0, float& p1) {
   p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 #ifndef VB200_ATTN_EMU_PAIRS
-#define VB200_ATTN_EMU_PAIRS 6      // of the 16 score pairs of a chunk, how many take ex2_poly2 instead of MUFU
+#define VB200_ATTN_EMU_PAIRS 4      // of the 16 score pairs of a chunk, how many take ex2_poly2 instead of MUFU
 #endif
 
-// 32 scores -> 32 probabilities (bf16, 16 TMEM columns); row sum tracked on two packed chains.
-__device__ __forceinline__ void exp_store_chunk(const uint32_t (&s)[32], uint32_t t_p_chunk, uint64_t scale2,
-                                                uint64_t mneg2, uint64_t (&ps)[2]) {
-  uint32_t pk[16];
+// 32 scores -> 32 probabilities (bf16 pairs in pk); row sum tracked on two packed chains.
+__device__ __forceinline__ void exp_chunk(const uint32_t (&s)[32], uint32_t (&pk)[16], uint64_t scale2,
+                                          uint64_t mneg2, uint64_t (&ps)[2]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const uint64_t x = ffma2(pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), scale2, mneg2);
@@ -167,6 +166,11 @@ __device__ __forceinline__ void exp_store_chunk(const uint32_t (&s)[32], uint32_
     ps[i & 1] = fadd2(ps[i & 1], pack2(p0, p1));
     pk[i] = pack_bf16x2(p0, p1);
   }
+}
+__device__ __forceinline__ void exp_store_chunk(const uint32_t (&s)[32], uint32_t t_p_chunk, uint64_t scale2,
+                                                uint64_t mneg2, uint64_t (&ps)[2]) {
+  uint32_t pk[16];
+  exp_chunk(s, pk, scale2, mneg2, ps);
   tmem_st_32x16(t_p_chunk, pk);
 }
 
@@ -255,6 +259,104 @@ __device__ __forceinline__ void softmax_block(uint32_t t_buf, uint32_t t_prev, u
     tmem_ld_wait();
     if (TAIL) max_chunk<true>(s, c * 32, last_valid, unused);
     exp_store_chunk(s, t_buf + c * 16, scale2, mneg2, ps);
+  }
+  float s0, s1, s2, s3;
+  unpack2(ps[0], s0, s1);
+  unpack2(ps[1], s2, s3);
+  l = fmaf(l, alpha, (s0 + s1) + (s2 + s3));
+  alpha_prev = alpha;
+}
+
+// 64-column TMEM load / 32-column store for the full-block path below
+__device__ __forceinline__ void tmem_ld_32x64(uint32_t taddr, uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+      "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,"
+      "%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+        "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+        "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+        "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+        "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32_lo(uint32_t taddr, const uint32_t (&r)[64]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
+      "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+      "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// A FULL key block (128 valid keys) handled in 64-score halves: twice the independent work between
+// two TMEM round trips as the 32-score chunks of the tail path.  The packed pair i replaces s[i]
+// (already consumed: pair i reads s[2i], s[2i+1]), so a half never needs more than its own 64
+// registers beside the 64 accumulators.
+__device__ __forceinline__ void softmax_block_full(uint32_t t_buf, uint32_t t_prev, uint64_t* pv_done_prev,
+                                                   uint32_t pv_parity, uint64_t* buf_free_prev, int lane, int j,
+                                                   float scale_log2, float& m, float& l, float& alpha_prev,
+                                                   uint64_t (&o)[32]) {
+  float bm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+  for (int hb = 0; hb < 2; ++hb) {
+    uint32_t s[64];
+    tmem_ld_32x64(t_buf + hb * 64, s);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+      bm[0] = fmaxf(bm[0], __uint_as_float(s[i]));     bm[1] = fmaxf(bm[1], __uint_as_float(s[i + 1]));
+      bm[2] = fmaxf(bm[2], __uint_as_float(s[i + 2])); bm[3] = fmaxf(bm[3], __uint_as_float(s[i + 3]));
+    }
+  }
+  const float m_new = fmaxf(m, fmaxf(fmaxf(bm[0], bm[1]), fmaxf(bm[2], bm[3])));
+  const float alpha = ex2_approx((m - m_new) * scale_log2);   // 0 on the first block (m = -inf)
+  m = m_new;
+  const float mneg = -m_new * scale_log2;
+  const uint64_t scale2 = pack2(scale_log2, scale_log2), mneg2 = pack2(mneg, mneg);
+  uint64_t ps[2] = {0ull, 0ull};
+#pragma unroll 1
+  for (int hb = 0; hb < 2; ++hb) {
+    if (hb == 1 && j > 0) {
+      // fold in O_blk(j-1) (its MMAs were issued a whole block ago) and hand its buffer back to the MMA warp
+      mbar_wait(pv_done_prev, pv_parity);
+      tc_fence_after();
+      fold_o_block(o, t_prev + 64, alpha_prev);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(buf_free_prev);
+    }
+    uint32_t s[64];
+    tmem_ld_32x64(t_buf + hb * 64, s);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const uint64_t x = ffma2(pack2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), scale2, mneg2);
+      const int ii = i & 15;
+      const bool emulate = ((ii + 1) * VB200_ATTN_EMU_PAIRS) / 16 != (ii * VB200_ATTN_EMU_PAIRS) / 16;
+      float p0, p1;
+      if (emulate) {
+        ex2_poly2(x, p0, p1);
+      } else {
+        float x0, x1;
+        unpack2(x, x0, x1);
+        p0 = ex2_approx(x0);
+        p1 = ex2_approx(x1);
+      }
+      ps[i & 1] = fadd2(ps[i & 1], pack2(p0, p1));
+      s[i] = pack_bf16x2(p0, p1);
+    }
+    tmem_st_32x32_lo(t_buf + hb * 32, s);
   }
   float s0, s1, s2, s3;
   unpack2(ps[0], s0, s1);
@@ -436,7 +538,11 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
       if (j > 0) { mbar_wait(pvd, pv_par); tc_fence_after(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bfr); }
       l = 1.f; (void)n_chunks; (void)t_buf; (void)t_prev; (void)m;
 #else
+#if defined(VB200_ATTN_CHUNK32)
       if (!tail) softmax_block<false>(t_buf, t_prev, pvd, pv_par, bfr, lane, j, 4, BKV, scale_log2, m, l, alpha_prev, o);
+#else
+      if (!tail) softmax_block_full(t_buf, t_prev, pvd, pv_par, bfr, lane, j, scale_log2, m, l, alpha_prev, o);
+#endif
       else softmax_block<true>(t_buf, t_prev, pvd, pv_par, bfr, lane, j, n_chunks, last_valid, scale_log2, m, l, alpha_prev, o);
 #endif
       tmem_st_wait();
