@@ -105,27 +105,6 @@ __device__ __forceinline__ float ex2_poly(float x) {
   p = fmaf(r, p, 0.99992806f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
-// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot per two lanes' worth of fp32 work.  The
-// exp pass is co-limited by instruction issue and MUFU.EX2, so halving the FMA-pipe instruction
-// count is what lets a larger share of the exponentials move off MUFU (tools/fma2_bench.cu).
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
-  uint64_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
 // two exponentials at once on the FMA / ALU pipes (same cubic as ex2_poly)
 __device__ __forceinline__ void ex2_poly2(uint64_t x, float& p0, float& p1) {
   float x0, x1;

@@ -318,6 +318,14 @@ __device__ __forceinline__ void unpack8(const Raw8<float>& r, float* v) {
   v[4] = __uint_as_float(r.b.x); v[5] = __uint_as_float(r.b.y); v[6] = __uint_as_float(r.b.z); v[7] = __uint_as_float(r.b.w);
 }
 
+// raw (unconverted) single logit, so that a prefetch never waits on the load it has just issued
+template <typename T> struct Raw1 { T v; };
+template <typename T>
+__device__ __forceinline__ Raw1<T> load_raw1(const T* p, int j) { return Raw1<T>{p[j]}; }
+__device__ __forceinline__ float cvt1(Raw1<float> r) { return r.v; }
+__device__ __forceinline__ float cvt1(Raw1<__half> r) { return __half2float(r.v); }
+__device__ __forceinline__ float cvt1(Raw1<__nv_bfloat16> r) { return __bfloat162float(r.v); }
+
 // ---------------------------------------------------------------- P, production form
 // Register-resident O(K) reverse step for K = 256*KC (<= 1024): one warp per token, the K logits
 // are read from HBM exactly once (16-byte loads), softmax statistics stay in registers, and the
@@ -331,6 +339,13 @@ __device__ __forceinline__ void unpack8(const Raw8<float>& r, float* v) {
 //   sum_j w_j = coef * Z + K * cst  (+ non-negative corrections dx, dm for the special classes)
 // is closed form; the per-class weights are only walked when the draw lands in the generic part.
 // Greedy mode (argmax of the same weights) needs no logarithm either.
+//
+// A warp walks its tokens in batches of 32.  Everything about a token that is not its logits —
+// timestep, x_t, the table-derived coefficients, the Philox draw — is produced LANE-PARALLEL at the
+// head of the batch (lane k prepares the batch's k-th token) and handed out with shuffles, so no
+// token waits on the utterance -> timestep -> table chain of dependent loads and the ten Philox
+// rounds cost 1/32 of a token each.  The logits of token k+1 (packed, unconverted) are in flight
+// while token k is reduced.
 template <typename T, int KC, int NOISE>
 __global__ void __launch_bounds__(256, 3) posterior_fast_kernel(
     int32_t* __restrict__ x_out, const T* __restrict__ logits, int64_t ld_logits,
@@ -341,170 +356,202 @@ __global__ void __launch_bounds__(256, 3) posterior_fast_kernel(
   constexpr int K = KC * 256;
   constexpr int NR = KC * 8;                  // logits per lane
   constexpr float kLog2e = 1.4426950408889634f;
+  constexpr unsigned kFull = 0xffffffffu;
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tok = n_rows * n_levels;
   const int stride = gridDim.x * warps_per_block;
-  int tok = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  // software pipeline over this warp's tokens: the next token's logits (still packed) and its two
-  // special-class logits are in flight while the current token is reduced
+  const int w0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const bool absorbing = transition == VB200_ABSORBING;
+  const int m_abs = absorbing ? K / 2 : -1;
+  const int m_probe = K / 2;                  // column read for the absorbing class (unused otherwise)
+
   Raw8<T> nxt[KC];
-  float nxt_lx = 0.f, nxt_lm = 0.f;
-  int nxt_xt = 0;
-  const int m_abs = K / 2;
-  auto prefetch = [&](int tk) {
+  Raw1<T> nxt_lx{}, nxt_lm{};
+  auto prefetch = [&](int tk, int xt) {
     const int rw = tk / n_levels, lv = tk - rw * n_levels;
     const T* lr = logits + static_cast<size_t>(rw) * ld_logits + static_cast<size_t>(lv) * K;
 #pragma unroll
     for (int c = 0; c < KC; ++c) nxt[c] = load_raw8<T>(lr + c * 256 + lane * 8);
-    nxt_xt = x_t_all[tk];
-    nxt_lx = load_logit<T>(lr, nxt_xt);
-    nxt_lm = load_logit<T>(lr, m_abs);
+    nxt_lx = load_raw1<T>(lr, xt);
+    nxt_lm = load_raw1<T>(lr, m_probe);
   };
-  if (tok < n_tok) prefetch(tok);
-  for (; tok < n_tok; tok += stride) {
-    const int row = tok / n_levels, level = tok - row * n_levels;
-    const int b = row_utt[row];
-    const int t = min(max(t_utt[b], 0), S - 1);
-    // lane owns classes j = c*256 + lane*8 + i  (c < KC, i < 8) in registers v[c*8 + i]
-    float v[NR];
-#pragma unroll
-    for (int c = 0; c < KC; ++c) unpack8(nxt[c], v + c * 8);
-    const int x_t = nxt_xt;
-    const float l_x = nxt_lx, l_m = nxt_lm;
-    if (tok + stride < n_tok) prefetch(tok + stride);
-    // Row max; the arg max (lowest index wins ties) is only needed for greedy decoding and for
-    // t == 0 (raw logits, no noise, ar_discrete.py:407,413), so the sampling path pays for a plain max.
-    Best top{-INFINITY, 0x7fffffff};
-    if (NOISE == VB200_NOISE_GREEDY || t == 0) {
-#pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const int j = (r >> 3) * 256 + lane * 8 + (r & 7);
-        if (v[r] > top.v) { top.v = v[r]; top.j = j; }   // ascending j inside a lane
-      }
-      top = warp_best(top);
-    } else {
-      float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
-#pragma unroll
-      for (int r = 4; r < NR; r += 4) {
-        m0 = fmaxf(m0, v[r]); m1 = fmaxf(m1, v[r + 1]); m2 = fmaxf(m2, v[r + 2]); m3 = fmaxf(m3, v[r + 3]);
-      }
-      top.v = warp_max(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
-    }
-    const float mx = top.v;
-    if (t == 0) {
-      if (lane == 0) x_out[tok] = top.j;
-      continue;
-    }
-    const float mx_l2 = -mx * kLog2e;
-    float part[KC];                                       // per-lane partial sums of e_j, one per 8-chunk
-    float lane_sum = 0.f;
-#pragma unroll
-    for (int c = 0; c < KC; ++c) {
-      float acc = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float e = exp2f_fast(fmaf(v[c * 8 + i], kLog2e, mx_l2));
-        v[c * 8 + i] = e;
-        acc += e;
-      }
-      part[c] = acc;
-      lane_sum += acc;
-    }
-    // inclusive warp scan of the lane sums (class order of the CDF = lane-major, any fixed order works)
-    float incl = lane_sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const float n = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += n;
-    }
-    const float Z = __shfl_sync(0xffffffffu, incl, 31);
-    const float invZ = 1.0f / Z;
 
-    const int t1 = t - 1;
-    const float* one = table + static_cast<size_t>(t) * VB200_TAB_STRIDE;
-    const float* cum = table + static_cast<size_t>(t1) * VB200_TAB_STRIDE;
-    const bool absorbing = transition == VB200_ABSORBING;
-    const int m = absorbing ? K / 2 : -1;
-    const bool at_m = x_t == m;
-    const float f1_self = (absorbing ? (at_m ? one[VB200_TAB_ONE_BOTH] : one[VB200_TAB_ONE_KEEP]) : one[VB200_TAB_ONE_KEEP]) + kEps;
-    const float f1_oth = (absorbing ? (at_m ? one[VB200_TAB_ONE_ABSORB] : one[VB200_TAB_ONE_OFF]) : one[VB200_TAB_ONE_OFF]) + kEps;
-    const float a_gen = cum[VB200_TAB_CUM_KEEP], c_gen = cum[VB200_TAB_CUM_OFF];
-    const float a_m = absorbing ? cum[VB200_TAB_CUM_BOTH] : a_gen, c_m = absorbing ? cum[VB200_TAB_CUM_ABSORB] : c_gen;
-    // generic class: w_j = coef * e_j + cst
-    const float coef = (a_gen - c_gen) * invZ * f1_oth;
-    const float cst = (c_gen + kEps) * f1_oth;
-    // special classes: true weight minus what the generic formula assigns them (>= 0)
-    const float e_x = exp2f_fast(fmaf(l_x, kLog2e, mx_l2));
-    const float ax = at_m ? a_m : a_gen, cx = at_m ? c_m : c_gen;
-    const float w_x = f1_self * (fmaf(e_x * invZ, ax - cx, cx) + kEps);
-    const float dx = fmaxf(w_x - fmaf(e_x, coef, cst), 0.f);
-    float w_m = 0.f, dm = 0.f;
-    if (absorbing && !at_m) {
-      const float e_m = exp2f_fast(fmaf(l_m, kLog2e, mx_l2));
-      w_m = f1_oth * (fmaf(e_m * invZ, a_m - c_m, c_m) + kEps);
-      dm = fmaxf(w_m - fmaf(e_m, coef, cst), 0.f);
-    }
-    int pick;
-    if (NOISE == VB200_NOISE_GREEDY) {
-      // generic weights are monotone in the logit, special classes only gain: compare three candidates
-      float best_w = fmaf(exp2f_fast(fmaf(top.v, kLog2e, mx_l2)), coef, cst);
-      pick = top.j;
-      if (top.j == x_t) best_w = w_x;
-      else if (top.j == m) best_w = w_m;
-      if (w_x > best_w || (w_x == best_w && x_t < pick)) { best_w = w_x; pick = x_t; }
-      if (absorbing && !at_m && (w_m > best_w || (w_m == best_w && m < pick))) { best_w = w_m; pick = m; }
-    } else {
-      const int32_t* ur = utt + static_cast<size_t>(b) * VB200_U_STRIDE;
-      const uint32_t gid = static_cast<uint32_t>(ur[VB200_U_GID]);
-      const uint32_t frame = static_cast<uint32_t>(row - ur[VB200_U_RESP0]);
-      const Philox ph{seed_lo, seed_hi};
-      const uint4 rnd = ph(0xC0DEu, frame * n_levels + level, gid, t);
-      const float w_generic = fmaf(coef, Z, static_cast<float>(K) * cst);
-      float target = u01(rnd.x) * (w_generic + dx + dm);
-      if (target < dx) {
-        pick = x_t;
-      } else if (target < dx + dm) {
-        pick = m;
-      } else {
-        target -= dx + dm;
-        // lane-level CDF of the generic weights: lane sum = coef * sum(e) + NR * cst
-        const float w_incl = fmaf(coef, incl, static_cast<float>((lane + 1) * NR) * cst);
-        const unsigned ball = __ballot_sync(0xffffffffu, target < w_incl);
-        const int src = ball ? __ffs(ball) - 1 : 31;      // rounding at the top end -> last lane
-        const float base = __shfl_sync(0xffffffffu, w_incl - fmaf(coef, lane_sum, static_cast<float>(NR) * cst), src);
-        int local = K - 1;
-        if (lane == src) {
-          float run = base;                                // cumulative weight before this lane
-          int c_sel = KC - 1;
-          bool done = false;
-#pragma unroll
-          for (int c = 0; c < KC - 1; ++c) {               // which 8-class chunk
-            const float nxt = run + fmaf(coef, part[c], 8.0f * cst);
-            if (!done) {
-              if (target < nxt) { c_sel = c; done = true; }
-              else run = nxt;
-            }
-          }
-          int i_sel = 7;                                   // rounding at the top end -> last class
-#pragma unroll
-          for (int c = 0; c < KC; ++c) {
-            if (c == c_sel) {
-              float r2 = run;
-              bool found = false;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                r2 += fmaf(coef, v[c * 8 + i], cst);
-                if (!found && target < r2) { found = true; i_sel = i; }
-              }
-            }
-          }
-          local = c_sel * 256 + lane * 8 + i_sel;
-        }
-        pick = __shfl_sync(0xffffffffu, local, src);
+#pragma unroll 1
+  for (int base = w0; base < n_tok; base += 32 * stride) {
+    // ---- lane-parallel: everything but the logits of token `mine`
+    const int mine = base + lane * stride;
+    int my_xt = 0, my_t = 0;
+    uint32_t my_rnd = 0;
+    float cA = 0.f, cC = 0.f, cF1s = 0.f, cDax = 0.f, cCx = 0.f, cAm = 0.f, cCm = 0.f;
+    if (mine < n_tok) {
+      const int row = mine / n_levels, level = mine - row * n_levels;
+      const int b = row_utt[row];
+      my_t = min(max(t_utt[b], 0), S - 1);
+      my_xt = x_t_all[mine];
+      const float* one = table + static_cast<size_t>(my_t) * VB200_TAB_STRIDE;
+      const float* cum = table + static_cast<size_t>(max(my_t - 1, 0)) * VB200_TAB_STRIDE;
+      const bool at_m = my_xt == m_abs;
+      const float f1_self = (absorbing && at_m ? one[VB200_TAB_ONE_BOTH] : one[VB200_TAB_ONE_KEEP]) + kEps;
+      const float f1_oth = (absorbing ? (at_m ? one[VB200_TAB_ONE_ABSORB] : one[VB200_TAB_ONE_OFF]) : one[VB200_TAB_ONE_OFF]) + kEps;
+      const float a_gen = cum[VB200_TAB_CUM_KEEP], c_gen = cum[VB200_TAB_CUM_OFF];
+      const float a_m = absorbing ? cum[VB200_TAB_CUM_BOTH] : a_gen, c_m = absorbing ? cum[VB200_TAB_CUM_ABSORB] : c_gen;
+      cA = (a_gen - c_gen) * f1_oth;              // generic class: w_j = cA / Z * e_j + cC
+      cC = (c_gen + kEps) * f1_oth;
+      cF1s = f1_self;                             // class x_t: w = cF1s * (e_x / Z * cDax + cCx)
+      cDax = at_m ? a_m - c_m : a_gen - c_gen;
+      cCx = (at_m ? c_m : c_gen) + kEps;
+      cAm = f1_oth * (a_m - c_m);                 // absorbing class (x_t != m): w = e_m / Z * cAm + cCm
+      cCm = f1_oth * (c_m + kEps);
+      if (NOISE == VB200_NOISE_PHILOX) {
+        const int32_t* ur = utt + static_cast<size_t>(b) * VB200_U_STRIDE;
+        const uint32_t gid = static_cast<uint32_t>(ur[VB200_U_GID]);
+        const uint32_t frame = static_cast<uint32_t>(row - ur[VB200_U_RESP0]);
+        const Philox ph{seed_lo, seed_hi};
+        my_rnd = ph(0xC0DEu, frame * n_levels + level, gid, my_t).x;
       }
     }
-    if (lane == 0) x_out[tok] = pick;
+    // x_t of the next batch's first token, so that the last prefetch of this batch has its column
+    const int nb = base + 32 * stride;
+    const int nb_xt = nb < n_tok ? x_t_all[nb] : 0;
+    if (base == w0) prefetch(base, __shfl_sync(kFull, my_xt, 0));
+
+#pragma unroll 1
+    for (int k = 0; k < 32; ++k) {
+      const int tok = base + k * stride;
+      if (tok >= n_tok) break;
+      const int t = __shfl_sync(kFull, my_t, k);
+      const int x_t = __shfl_sync(kFull, my_xt, k);
+      // lane owns classes j = c*256 + lane*8 + i  (c < KC, i < 8) in registers v[c*8 + i]
+      float v[NR];
+#pragma unroll
+      for (int c = 0; c < KC; ++c) unpack8(nxt[c], v + c * 8);
+      const float l_x = cvt1(nxt_lx), l_m = cvt1(nxt_lm);
+      if (tok + stride < n_tok) {
+        const int xt_next = __shfl_sync(kFull, my_xt, (k + 1) & 31);
+        prefetch(tok + stride, k == 31 ? nb_xt : xt_next);
+      }
+      // Row max; the arg max (lowest index wins ties) is only needed for greedy decoding and for
+      // t == 0 (raw logits, no noise, ar_discrete.py:407,413), so the sampling path pays for a plain max.
+      Best top{-INFINITY, 0x7fffffff};
+      if (NOISE == VB200_NOISE_GREEDY || t == 0) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+          const int j = (r >> 3) * 256 + lane * 8 + (r & 7);
+          if (v[r] > top.v) { top.v = v[r]; top.j = j; }   // ascending j inside a lane
+        }
+        top = warp_best(top);
+      } else {
+        float m0 = v[0], m1 = v[1], m2 = v[2], m3 = v[3];
+#pragma unroll
+        for (int r = 4; r < NR; r += 4) {
+          m0 = fmaxf(m0, v[r]); m1 = fmaxf(m1, v[r + 1]); m2 = fmaxf(m2, v[r + 2]); m3 = fmaxf(m3, v[r + 3]);
+        }
+        top.v = warp_max(fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+      }
+      const float mx = top.v;
+      if (t == 0) {
+        if (lane == 0) x_out[tok] = top.j;
+        continue;
+      }
+      const float mx_l2 = -mx * kLog2e;
+      const uint64_t l2e2 = pack2(kLog2e, kLog2e), mxl2 = pack2(mx_l2, mx_l2);
+      float part[KC];                                       // per-lane partial sums of e_j, one per 8-chunk
+      float lane_sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < KC; ++c) {
+        uint64_t acc = 0ull;
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          float x0, x1;
+          unpack2(ffma2(pack2(v[c * 8 + i], v[c * 8 + i + 1]), l2e2, mxl2), x0, x1);
+          const float e0 = exp2f_fast(x0), e1 = exp2f_fast(x1);
+          v[c * 8 + i] = e0;
+          v[c * 8 + i + 1] = e1;
+          acc = fadd2(acc, pack2(e0, e1));
+        }
+        float a0, a1;
+        unpack2(acc, a0, a1);
+        part[c] = a0 + a1;
+        lane_sum += part[c];
+      }
+      // inclusive warp scan of the lane sums (class order of the CDF = lane-major, any fixed order works)
+      float incl = lane_sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += n;
+      }
+      const float Z = __shfl_sync(kFull, incl, 31);
+      const float invZ = 1.0f / Z;
+
+      const bool at_m = x_t == m_abs;
+      const bool has_m = absorbing && !at_m;
+      const float coef = __shfl_sync(kFull, cA, k) * invZ;        // generic class: w_j = coef * e_j + cst
+      const float cst = __shfl_sync(kFull, cC, k);
+      // special classes: true weight minus what the generic formula assigns them (>= 0)
+      const float e_x = exp2f_fast(fmaf(l_x, kLog2e, mx_l2));
+      const float w_x = __shfl_sync(kFull, cF1s, k) *
+                        fmaf(e_x * invZ, __shfl_sync(kFull, cDax, k), __shfl_sync(kFull, cCx, k));
+      const float dx = fmaxf(w_x - fmaf(e_x, coef, cst), 0.f);
+      const float e_m = exp2f_fast(fmaf(l_m, kLog2e, mx_l2));
+      const float w_m_all = fmaf(e_m * invZ, __shfl_sync(kFull, cAm, k), __shfl_sync(kFull, cCm, k));
+      const float w_m = has_m ? w_m_all : 0.f;
+      const float dm = has_m ? fmaxf(w_m_all - fmaf(e_m, coef, cst), 0.f) : 0.f;
+      int pick;
+      if (NOISE == VB200_NOISE_GREEDY) {
+        // generic weights are monotone in the logit, special classes only gain: compare three candidates
+        float best_w = fmaf(exp2f_fast(fmaf(top.v, kLog2e, mx_l2)), coef, cst);
+        pick = top.j;
+        if (top.j == x_t) best_w = w_x;
+        else if (top.j == m_abs) best_w = w_m;
+        if (w_x > best_w || (w_x == best_w && x_t < pick)) { best_w = w_x; pick = x_t; }
+        if (has_m && (w_m > best_w || (w_m == best_w && m_abs < pick))) { best_w = w_m; pick = m_abs; }
+      } else {
+        const uint32_t rnd = __shfl_sync(kFull, my_rnd, k);
+        const float w_generic = fmaf(coef, Z, static_cast<float>(K) * cst);
+        float target = u01(rnd) * (w_generic + dx + dm);
+        if (target < dx) {
+          pick = x_t;
+        } else if (target < dx + dm) {
+          pick = m_abs;
+        } else {
+          target -= dx + dm;
+          // lane-level CDF of the generic weights: lane sum = coef * sum(e) + NR * cst
+          const float w_incl = fmaf(coef, incl, static_cast<float>((lane + 1) * NR) * cst);
+          const unsigned ball = __ballot_sync(kFull, target < w_incl);
+          const int src = ball ? __ffs(ball) - 1 : 31;      // rounding at the top end -> last lane
+          // every lane walks its own 32 classes (branch-free, no divergence); the owner's answer is kept
+          float run = w_incl - fmaf(coef, lane_sum, static_cast<float>(NR) * cst);   // weight before this lane
+          int c_sel = 0;
+          {
+            float cum = run;
+#pragma unroll
+            for (int c = 0; c < KC - 1; ++c) {               // which 8-class chunk
+              cum += fmaf(coef, part[c], 8.0f * cst);
+              const bool past = target >= cum;
+              c_sel += past ? 1 : 0;
+              run = past ? cum : run;
+            }
+          }
+          float e8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            e8[i] = v[i];
+#pragma unroll
+            for (int c = 1; c < KC; ++c) e8[i] = c_sel == c ? v[c * 8 + i] : e8[i];
+          }
+          int i_sel = 0;                                     // prefix sums are monotone: count those <= target
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {                      // rounding at the top end -> last class
+            run += fmaf(coef, e8[i], cst);
+            i_sel += target >= run ? 1 : 0;
+          }
+          pick = __shfl_sync(kFull, c_sel * 256 + lane * 8 + i_sel, src);
+        }
+      }
+      if (lane == 0) x_out[tok] = pick;
+    }
   }
 }
 
