@@ -170,6 +170,29 @@ int vb200_posterior_sample_from_logits(int32_t* x_out, float* post_out, const vo
                                        vb200_noise noise, const float* uniforms, uint64_t seed,
                                        vb200_stream_t stream);
 
+/* H1 + P in one call (reference base.py:355,440 followed by
+ * ar_discrete.py:347-375,401-420): logits = head_in (n_rows, d) bf16 x W (n_levels*K, d)^T + bias,
+ * written to the caller's scratch `logits` (n_rows, n_levels*K) of logits_dtype, then the reverse
+ * step of vb200_posterior_sample_from_logits on them, both stream-ordered.  Two launches: a
+ * single-kernel epilogue fusion was analysed and rejected (the two-pass recompute
+ * costs more tensor time than the logits round trip it saves). */
+int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_dtype logits_dtype,
+                                const void* head_in_bf16, const void* W_bf16, const float* bias,
+                                int32_t n_rows, int32_t d, int32_t n_levels, int32_t K,
+                                const int32_t* x_t, const int32_t* row_utt, const int32_t* t_utt,
+                                const int32_t* utt, const float* table, int32_t S,
+                                vb200_transition tr, vb200_noise noise, const float* uniforms,
+                                uint64_t seed, vb200_stream_t stream);
+
+/* Scratch the caller provides for one denoiser forward over M packed rows, M_resp of them response
+ * rows (the library never allocates; reference: the activations of Base.forward base.py:427-443).
+ * sizes[7] receives the byte sizes, each rounded up to 256 B, in this order:
+ *   x fp32 (M, d) | h bf16 (M, d) | qkv bf16 (M, 3d) | att bf16 (M, d) | ff bf16 (M, 4d) |
+ *   head_in bf16 (M_resp, d) | logits logits_dtype (M_resp, n_out).
+ * Returns their sum, or a negative vb200_status. */
+int64_t vb200_workspace_bytes(int64_t M, int64_t M_resp, int32_t d, int32_t n_out,
+                              vb200_dtype logits_dtype, int64_t* sizes);
+
 /* reverse-loop helper (ar_discrete.py:750): t_utt[b] -= 1 for all b, on device (graph-capturable) */
 int vb200_step_timesteps(int32_t* t_utt, int32_t B, int32_t delta, vb200_stream_t stream);
 

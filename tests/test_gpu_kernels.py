@@ -328,3 +328,35 @@ def test_fast_posterior_kernel_matches_generic(L, transition, K):
             chi2 += (rest_obs - rest_exp) ** 2 / rest_exp
         dof = max(int(keep.sum().item()), 2)
         assert chi2 < dof + 6 * math.sqrt(2 * dof), (transition, K, xt_val, chi2, dof)
+
+
+def test_head_posterior_sample_equals_separate_calls(L):
+    """vb200_head_posterior_sample (SURVEY §8a rows H1 + P in one C call) against classifier GEMM
+    followed by vb200_posterior_sample_from_logits: same logits, same codes, bit for bit."""
+    from vall_e.vall_e import d3pm as pd
+    S, K, levels, d, rows, B = 30, 256, 8, 128, 333, 5
+    g = torch.Generator().manual_seed(11)
+    table = pd.scalar_table(S, K, "absorbing").to(DEV)
+    head_in = torch.randn(rows, d, generator=g).bfloat16().to(DEV)
+    W = (torch.randn(levels * K, d, generator=g) * 0.2).bfloat16().to(DEV)
+    bias = torch.randn(levels * K, generator=g).to(DEV)
+    x_t = torch.randint(0, K, (rows, levels), generator=g, dtype=torch.int32)
+    x_t[::2] = K // 2
+    x_t = x_t.to(DEV)
+    row_utt = (torch.arange(rows, dtype=torch.int32) % B).sort().values.to(DEV)
+    t_utt = torch.tensor([1, 7, 15, 28, 29], dtype=torch.int32, device=DEV)
+    utt = torch.zeros(B, L.U_STRIDE, dtype=torch.int32, device=DEV)
+    utt[:, L.U_GID] = torch.arange(B, dtype=torch.int32, device=DEV) + 100
+    for noise in (L.NOISE_PHILOX, L.NOISE_GREEDY):
+        lg_a = torch.empty(rows, levels * K, dtype=torch.float16, device=DEV)
+        lg_b = torch.empty_like(lg_a)
+        out_a = torch.empty(rows, levels, dtype=torch.int32, device=DEV)
+        out_b = torch.empty_like(out_a)
+        L.head_posterior_sample(out_a, lg_a, head_in, W, bias, x_t, row_utt, t_utt, utt, table, levels, K,
+                                L.ABSORBING, noise, seed=3)
+        L.gemm_bf16(lg_b, head_in, W, bias, None, L.EPI_BIAS)
+        L.posterior_sample_from_logits(out_b, None, lg_b, levels * K, x_t, row_utt, t_utt, utt, table, rows,
+                                       levels, K, L.ABSORBING, noise, seed=3)
+        assert torch.equal(lg_a, lg_b)
+        assert torch.equal(out_a, out_b)
+        assert 0 <= int(out_a.min()) and int(out_a.max()) < K

@@ -21,10 +21,26 @@ def built_lib():
     return build.build()
 
 
+def test_workspace_bytes_matches_the_layout_the_engine_carves(built_lib):
+    """vb200_workspace_bytes is a host-only call: sizes in WS_FIELDS order, 256-byte granules."""
+    import torch
+    from vall_e.b200 import lib as L
+    M, Mr, d, n_out = 1027, 750, 1024, 8192
+    total, sizes = L.workspace_bytes(M, Mr, d, n_out, torch.float16)
+    raw = [M * d * 4, M * d * 2, M * 3 * d * 2, M * d * 2, M * 4 * d * 2, Mr * d * 2, Mr * n_out * 2]
+    assert len(sizes) == len(L.WS_FIELDS) == 7
+    assert all(s % 256 == 0 and 0 <= s - r < 256 for s, r in zip(sizes, raw))
+    assert total == sum(sizes)
+    assert L.workspace_bytes(0, 0, d, n_out, torch.float32) == (0, [0] * 7)
+    assert L.workspace_bytes(M, Mr, d, n_out, torch.float32)[1][6] == (Mr * n_out * 4 + 255) // 256 * 256
+    with pytest.raises(L.VB200Error):
+        L.workspace_bytes(10, 11, d, n_out, torch.float16)      # more response rows than rows
+
+
 def test_library_exports_every_declared_symbol(built_lib):
     header = (ROOT / "include" / "vb200.h").read_text()
     declared = set(re.findall(r"\b(vb200_[a-z0-9_]+)\s*\(", header)) - {"vb200_stream_t"}
-    assert len(declared) >= 14
+    assert len(declared) >= 16
     lib = ctypes.CDLL(str(built_lib))
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/vb200.h but not exported"

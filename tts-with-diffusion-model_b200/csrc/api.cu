@@ -126,3 +126,37 @@ extern "C" int vb200_device_sms(void) {
     return VB200_ERR_CUDA;
   return sms;
 }
+
+extern "C" int64_t vb200_workspace_bytes(int64_t M, int64_t M_resp, int32_t d, int32_t n_out,
+                                         vb200_dtype logits_dtype, int64_t* sizes) {
+  using namespace vb200;
+  if (M < 0 || M_resp < 0 || M_resp > M || d <= 0 || n_out <= 0 || !sizes) {
+    set_error("workspace_bytes: bad sizes M=%lld M_resp=%lld d=%d n_out=%d", static_cast<long long>(M),
+              static_cast<long long>(M_resp), d, n_out);
+    return VB200_ERR_INVALID;
+  }
+  const int64_t lsz = logits_dtype == VB200_F32 ? 4 : 2;
+  const int64_t raw[7] = {M * d * 4, M * d * 2, M * 3 * d * 2, M * d * 2, M * 4 * d * 2,
+                          M_resp * d * 2, M_resp * n_out * lsz};
+  int64_t total = 0;
+  for (int i = 0; i < 7; ++i) {
+    sizes[i] = (raw[i] + 255) & ~static_cast<int64_t>(255);
+    total += sizes[i];
+  }
+  return total;
+}
+
+extern "C" int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_dtype logits_dtype,
+                                           const void* head_in_bf16, const void* W_bf16, const float* bias,
+                                           int32_t n_rows, int32_t d, int32_t n_levels, int32_t K,
+                                           const int32_t* x_t, const int32_t* row_utt, const int32_t* t_utt,
+                                           const int32_t* utt, const float* table, int32_t S,
+                                           vb200_transition tr, vb200_noise noise, const float* uniforms,
+                                           uint64_t seed, vb200_stream_t stream) {
+  const int rc = vb200_gemm_bf16(logits, logits_dtype, head_in_bf16, W_bf16, bias, nullptr, n_rows,
+                                 n_levels * K, d, VB200_EPI_BIAS, stream);
+  if (rc != VB200_OK) return rc;
+  return vb200_posterior_sample_from_logits(x_out, nullptr, logits, logits_dtype,
+                                            static_cast<int64_t>(n_levels) * K, x_t, row_utt, t_utt, utt,
+                                            table, n_rows, n_levels, K, S, tr, noise, uniforms, seed, stream);
+}

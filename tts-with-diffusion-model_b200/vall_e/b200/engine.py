@@ -168,14 +168,24 @@ class DenoiserEngine:
         d, M, Mr = w.d, lay.M, lay.M_resp
         e = lambda *s, dt: torch.empty(*s, dtype=dt, device=dev)
         w.ensure_pe(lay.max_T)
-        return Workspace(
-            x=e(M, d, dt=torch.float32), h=e(M, d, dt=torch.bfloat16), qkv=e(M, 3 * d, dt=torch.bfloat16),
-            att=e(M, d, dt=torch.bfloat16), ff=e(M, 4 * d, dt=torch.bfloat16),
-            head_in=e(Mr, d, dt=torch.bfloat16), logits=e(Mr, w.n_out, dt=logits_dtype or self.logits_dtype))
+        # one allocation, carved up the way the C ABI sizes it (vb200_workspace_bytes)
+        ldt = logits_dtype or self.logits_dtype
+        total, sizes = L.workspace_bytes(M, Mr, d, w.n_out, ldt)
+        flat = e(max(total, 1), dt=torch.uint8)
+        shapes = {"x": ((M, d), torch.float32), "h": ((M, d), torch.bfloat16), "qkv": ((M, 3 * d), torch.bfloat16),
+                  "att": ((M, d), torch.bfloat16), "ff": ((M, 4 * d), torch.bfloat16),
+                  "head_in": ((Mr, d), torch.bfloat16), "logits": ((Mr, w.n_out), ldt)}
+        views, off = {}, 0
+        for name, size in zip(L.WS_FIELDS, sizes):
+            shape, dt = shapes[name]
+            n = shape[0] * shape[1] * torch.empty((), dtype=dt).element_size()
+            views[name] = flat[off:off + n].view(dt).view(shape)
+            off += size
+        return Workspace(extra={"flat": flat}, **views)
 
     # ------------------------------------------------------------------ one denoiser forward
     def forward(self, lay: BatchLayout, ws: Workspace, resp_ids: torch.Tensor, level_utt: torch.Tensor,
-                use_time: bool, hidden_out: list | None = None) -> torch.Tensor:
+                use_time: bool, hidden_out: list | None = None, head: bool = True) -> torch.Tensor:
         """resp_ids int32 (M_resp, levels_in); level_utt int32 (B) = AdaLN row (and time_emb row when
         use_time).  Returns ws.logits (M_resp, n_out): classifier(x) on the response rows."""
         w = self.w
@@ -200,8 +210,11 @@ class DenoiserEngine:
             if hidden_out is not None:
                 hidden_out.append(ws.x.clone())
         L.gather_rows_bf16(ws.head_in, ws.x, lay.resp_row_index)
+        self.launches += 1 + 7 * len(w.layers) + 1
+        if not head:              # the caller runs classifier + reverse step as one C call
+            return ws.head_in
         gemm(ws.logits, ws.head_in, w.w_cls, w.b_cls, epi=L.EPI_BIAS)
-        self.launches += 1 + 7 * len(w.layers) + 2
+        self.launches += 1
         return ws.logits
 
     def _gemm(self, out, A, W, bias=None, residual=None, epi=L.EPI_NONE):
@@ -292,9 +305,15 @@ class Session:
         t_utt.fill_(timesteps - 1)
 
         def one_step(uniforms=None):
-            logits = eng.forward(lay, ws, x_t, t_utt, use_time=True)
-            L.posterior_sample_from_logits(x_t, None, logits, w.n_out, x_t, lay.resp_row_utt, t_utt, lay.utt,
-                                           table, lay.M_resp, n_levels, K, transition, noise, uniforms, seed)
+            if eng.profile is None and not eng.simt:
+                head_in = eng.forward(lay, ws, x_t, t_utt, use_time=True, head=False)
+                L.head_posterior_sample(x_t, ws.logits, head_in, w.w_cls, w.b_cls, x_t, lay.resp_row_utt, t_utt,
+                                        lay.utt, table, n_levels, K, transition, noise, uniforms, seed)
+                eng.launches += 1
+            else:                 # per-launch timing hooks / CUDA-core validation path: separate calls
+                logits = eng.forward(lay, ws, x_t, t_utt, use_time=True)
+                L.posterior_sample_from_logits(x_t, None, logits, w.n_out, x_t, lay.resp_row_utt, t_utt, lay.utt,
+                                               table, lay.M_resp, n_levels, K, transition, noise, uniforms, seed)
             L.step_timesteps(t_utt, -1)
             eng.launches += 2
 

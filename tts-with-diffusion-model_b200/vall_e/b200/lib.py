@@ -44,6 +44,10 @@ PROTOTYPES = {
     "vb200_posterior_sample_from_logits": (
         [_p, _p, _p, C.c_int, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, C.c_int, C.c_int, _p, _u64, _p],
         C.c_int),
+    "vb200_head_posterior_sample": (
+        [_p, _p, C.c_int, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, C.c_int, C.c_int, _p, _u64, _p],
+        C.c_int),
+    "vb200_workspace_bytes": ([_i64, _i64, _i32, _i32, C.c_int, C.POINTER(C.c_int64)], C.c_int64),
     "vb200_step_timesteps": ([_p, _i32, _i32, _p], C.c_int),
 }
 
@@ -157,6 +161,28 @@ def posterior_sample_from_logits(x_out, post_out, logits, ld_logits, x_t, row_ut
         ptr(x_out), ptr(post_out), ptr(logits), dtype_code(logits.dtype), ld_logits, ptr(x_t),
         ptr(row_utt), ptr(t_utt), ptr(utt), ptr(table), n_rows, n_levels, K, table.shape[0], transition,
         noise, ptr(uniforms), seed, stream()), "vb200_posterior_sample_from_logits")
+
+
+def head_posterior_sample(x_out, logits, head_in, W, bias, x_t, row_utt, t_utt, utt, table, n_levels, K,
+                          transition, noise, uniforms=None, seed=0):
+    """classifier GEMM into the caller's `logits` scratch + reverse step on them (one C call)."""
+    n_rows, d = head_in.shape
+    _check(load().vb200_head_posterior_sample(
+        ptr(x_out), ptr(logits), dtype_code(logits.dtype), ptr(head_in), ptr(W), ptr(bias), n_rows, d,
+        n_levels, K, ptr(x_t), ptr(row_utt), ptr(t_utt), ptr(utt), ptr(table), table.shape[0], transition,
+        noise, ptr(uniforms), seed, stream()), "vb200_head_posterior_sample")
+
+
+WS_FIELDS = ("x", "h", "qkv", "att", "ff", "head_in", "logits")
+
+
+def workspace_bytes(M, M_resp, d, n_out, logits_dtype):
+    """(total, sizes[7]) of the scratch one denoiser forward needs, in WS_FIELDS order (host-only call)."""
+    sizes = (C.c_int64 * 7)()
+    total = load().vb200_workspace_bytes(M, M_resp, d, n_out, dtype_code(logits_dtype), sizes)
+    if total < 0:
+        raise VB200Error(f"vb200_workspace_bytes failed with status {total}: {last_error()}")
+    return int(total), [int(v) for v in sizes]
 
 
 def step_timesteps(t_utt, delta):
