@@ -20,18 +20,20 @@
 namespace vb200 {
 
 namespace gemm {
-constexpr int BM = 128, BN = 256, BK = 64;
+constexpr int BM = 128, BK = 64;   // BN (256, or 128 for small problems) is a kernel template parameter
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 // CTAS = 1: one CTA per 128x256 tile, stage = A 16 KB + W 32 KB, 4 stages.
 // CTAS = 2: a CTA pair (cluster of 2, cta_group::2) per 256x256 tile; each CTA stages its own 128
 //           rows of A and HALF of the W tile (128 rows), 32 KB per stage, 6 stages.  The pair's
 //           tensor cores read both halves, which halves every SM's shared-memory operand traffic —
 //           measured necessary: a lone CTA sustains 163 cycles per 128x256x16 MMA against 128 nominal.
-template <int CTAS> struct Cfg {
+// CTAS = 1, BN = 128: narrow tiles for problems with fewer 128x256 tiles than SMs (one utterance
+//           at a time: M ~ 1000) — twice the CTAs, 32 KB stages, 6 stages.
+template <int CTAS, int BN> struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = CTAS == 1 ? 4 : 6;
+  static constexpr int STAGES = STAGE_BYTES == 48 * 1024 ? 4 : 6;
 };
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;   // 320
@@ -57,12 +59,38 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaxf(x, 0.0f) - fabsf(x * q);
 }
 
-template <int EPI, typename OutT, int CTAS>
+// Two at once with packed f32x2 arithmetic (FFMA2: half the issue slots of the polynomial), written
+// as gelu(x) = x * (0.5 + copysign(0.5 - q, x)) — the same q as above.  With the scalar form the
+// epilogue of the FFN1 GEMM (K = 1024) took longer than the tile's MMAs (tensor pipe 86 % active).
+__device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
+  const float z0 = fminf(fabsf(x0) * 0.70710678118654752f, 6.0f);
+  const float z1 = fminf(fabsf(x1) * 0.70710678118654752f, 6.0f);
+  const uint64_t z = pack2(z0, z1);
+  uint64_t p = ffma2(z, pack2(9.22344479e-05f, 9.22344479e-05f), pack2(-2.20238999e-03f, -2.20238999e-03f));
+  p = ffma2(z, p, pack2(2.23510694e-02f, 2.23510694e-02f));
+  p = ffma2(z, p, pack2(-1.29628107e-01f, -1.29628107e-01f));
+  p = ffma2(z, p, pack2(-9.38564420e-01f, -9.38564420e-01f));
+  p = ffma2(z, p, pack2(-1.62045550e+00f, -1.62045550e+00f));
+  p = ffma2(z, p, pack2(-1.00044155e+00f, -1.00044155e+00f));
+  float p0, p1, q0, q1, h0, h1;
+  unpack2(p, p0, p1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(p0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(p1));
+  unpack2(ffma2(pack2(q0, q1), pack2(-1.0f, -1.0f), pack2(0.5f, 0.5f)), h0, h1);   // 0.5 - q >= 0
+  h0 = __uint_as_float(__float_as_uint(h0) | (__float_as_uint(x0) & 0x80000000u));
+  h1 = __uint_as_float(__float_as_uint(h1) | (__float_as_uint(x1) & 0x80000000u));
+  const uint64_t s = fadd2(pack2(h0, h1), pack2(0.5f, 0.5f));
+  unpack2(ffma2(pack2(x0, x1), s, 0ull), x0, x1);
+}
+
+template <int EPI, typename OutT, int CTAS, int BN>
 __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
     const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N, int K) {
   using namespace gemm;
-  constexpr int STAGES = Cfg<CTAS>::STAGES, STAGE_BYTES = Cfg<CTAS>::STAGE_BYTES, B_ROWS = Cfg<CTAS>::B_ROWS;
+  using C = Cfg<CTAS, BN>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_ROWS = C::B_ROWS;
+  constexpr int HALF_COLS = BN / 2;            // accumulator columns per epilogue warp
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0;       // 0 = leader of the pair
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -173,13 +201,13 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     // -------------------------------------------------------------- epilogue warps
     const int e = warp - 2;
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
-    const int half = e >> 2;                   // which 128 of the 256 accumulator columns
+    const int half = e >> 2;                   // which half of the BN accumulator columns
     uint8_t* stage_tile = epi_smem + e * EPI_TILE_BYTES;
     uint8_t* my_row = stage_tile + lane * 128;
     const int sw = lane & 7;                   // SWIZZLE_128B: 16-byte chunk index ^= row % 8
     constexpr bool kWide = sizeof(OutT) == 4;  // fp32: 32 columns per 128-byte row, else 64
     constexpr int CHUNK_COLS = kWide ? 32 : 64;
-    constexpr int CHUNKS = 128 / CHUNK_COLS;
+    constexpr int CHUNKS = HALF_COLS / CHUNK_COLS;
     const bool epi_leader = elect_one();       // the lane that owns this warp's bulk-store group
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
@@ -189,10 +217,10 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const int row0 = (m_blk * CTAS + cta_rank) * BM + quad * 32;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * 128;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * HALF_COLS;
 #pragma unroll 1
       for (int c = 0; c < CHUNKS; ++c) {
-        const int n0 = n_blk * BN + half * 128 + c * CHUNK_COLS;
+        const int n0 = n_blk * BN + half * HALF_COLS + c * CHUNK_COLS;
         if (epi_leader) tma_store_wait_read();  // previous store has finished reading the staging tile
         __syncwarp();
 #pragma unroll
@@ -209,7 +237,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nb + i));
-                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                unpack2(fadd2(pack2(v[i], v[i + 1]), pack2(b4.x, b4.y)), v[i], v[i + 1]);
+                unpack2(fadd2(pack2(v[i + 2], v[i + 3]), pack2(b4.z, b4.w)), v[i + 2], v[i + 3]);
               }
             } else {
 #pragma unroll
@@ -218,7 +247,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
           }
           if (EPI == VB200_EPI_BIAS_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i]);
+            for (int i = 0; i < 32; i += 2) gelu_erf_fast2(v[i], v[i + 1]);
           }
           if (kWide) {
 #pragma unroll
@@ -273,33 +302,48 @@ template <int EPI, typename OutT>
 static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, const float* bias, int M, int N,
                        int K, cudaStream_t st) {
   using namespace gemm;
-  // CTA pairs are faster per MMA (~135 vs 163 cycles) but halve the number of schedulable tiles;
-  // pick by estimated waves x cycles.  VB200_GEMM_CTAS=1|2 forces one kernel (A/B measurements).
+  // Three tilings, picked by estimated waves x cycles per k-step (tools/mma_bench.cu):
+  //   CTA pair 256x256 (~135 cycles, half as many schedulable units), one CTA 128x256 (~163),
+  //   one CTA 128x128 (~99, twice the tiles: for one utterance at a time, M ~ 1000).
+  // VB200_GEMM_CTAS=1|2 forces the CTA count (A/B measurements).
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("VB200_GEMM_CTAS");
     forced = e ? atoi(e) : 0;
   }
+  constexpr int BN = 256;
+  const int sms = num_sms(), mt = (M + BM - 1) / BM, nn = (N + BN - 1) / BN;
+  const long t_wide = static_cast<long>((mt * nn + sms - 1) / sms) * 163;
+  const long t_pair = static_cast<long>((((M + 2 * BM - 1) / (2 * BM)) * nn + sms / 2 - 1) / (sms / 2)) * 135;
+  const long t_narrow = N > 128 ? static_cast<long>((mt * ((N + 127) / 128) + sms - 1) / sms) * 99 : (1l << 40);
   int ctas = forced;
+  bool narrow = false;
   if (ctas != 1 && ctas != 2) {
-    const int nn = (N + BN - 1) / BN, sms = num_sms();
-    const long t1 = static_cast<long>(((M + BM - 1) / BM) * nn + sms - 1) / sms * 163;
-    const long t2 = static_cast<long>(((M + 2 * BM - 1) / (2 * BM)) * nn + sms / 2 - 1) / (sms / 2) * 135;
-    ctas = t2 <= t1 ? 2 : 1;
+    ctas = t_pair <= t_wide ? 2 : 1;
+    if (t_narrow < (ctas == 2 ? t_pair : t_wide)) { ctas = 1; narrow = true; }
   }
+  const int bn = narrow ? 128 : BN;
   CUtensorMap ta, tb, tout;
   int rc = cached_tmap(&ta, VB200_BF16, A, K, M, static_cast<uint64_t>(K) * 2, BK, BM);
   if (rc != VB200_OK) return rc;
-  rc = cached_tmap(&tb, VB200_BF16, W, K, N, static_cast<uint64_t>(K) * 2, BK, BN / ctas);
+  rc = cached_tmap(&tb, VB200_BF16, W, K, N, static_cast<uint64_t>(K) * 2, BK, bn / ctas);
   if (rc != VB200_OK) return rc;
   const int esz = sizeof(OutT);   // store box: 32 rows x 128 bytes
   rc = cached_tmap(&tout, dt, out, N, M, static_cast<uint64_t>(N) * esz, 128 / esz, 32);
   if (rc != VB200_OK) return rc;
-  const int tiles = ((M + BM * ctas - 1) / (BM * ctas)) * ((N + BN - 1) / BN);
+  const int tiles = ((M + BM * ctas - 1) / (BM * ctas)) * ((N + bn - 1) / bn);
   const int groups = num_sms() / ctas;
   const int grid = (tiles < groups ? tiles : groups) * ctas;
-  if (ctas == 1) {
-    auto kern = gemm_tcgen05_kernel<EPI, OutT, 1>;
+  if (narrow) {
+    auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 128>;
+    static bool configured = false;
+    if (!configured) {
+      VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      configured = true;
+    }
+    kern<<<grid, THREADS, SMEM_BYTES, st>>>(ta, tb, tout, bias, M, N, K);
+  } else if (ctas == 1) {
+    auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 256>;
     static bool configured = false;
     if (!configured) {
       VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -307,7 +351,7 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
     }
     kern<<<grid, THREADS, SMEM_BYTES, st>>>(ta, tb, tout, bias, M, N, K);
   } else {
-    auto kern = gemm_tcgen05_kernel<EPI, OutT, 2>;
+    auto kern = gemm_tcgen05_kernel<EPI, OutT, 2, 256>;
     static bool configured = false;
     if (!configured) {
       VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
