@@ -278,10 +278,10 @@ extern "C" int vb200_adaln(void* out_bf16, const float* x, const float* table,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
   if (d % 256 == 0 && d <= 1024) {
-    // contiguous row ranges per warp; enough warps for ~4 resident blocks per SM
+    // contiguous row ranges per warp; enough warps for ~4 resident blocks per SM.  Small M (one
+    // utterance at a time) gets one row per warp: there the kernel is latency-, not bandwidth-bound.
     const int total_warps = num_sms() * 4 * 8;
-    int rpw = (M + total_warps - 1) / total_warps;
-    if (rpw < 4) rpw = 4;
+    const int rpw = (M + total_warps - 1) / total_warps;
     const int warps = (M + rpw - 1) / rpw;
     const int grid = (warps + 7) / 8;
     switch (d / 256) {
