@@ -7,6 +7,8 @@
 #include <mutex>
 #include <tuple>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace vb200 {
@@ -115,6 +117,17 @@ int cached_tmap(CUtensorMap* out, vb200_dtype dtype, const void* ptr, uint64_t i
   return VB200_OK;
 }
 
+}  // namespace vb200
+
+namespace vb200 {
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VB200_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 }  // namespace vb200
 
 extern "C" const char* vb200_last_error(void) { return vb200::g_err; }

@@ -398,6 +398,9 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: cu_rows (static batch layout) was read above; qkv and `out` only from here on
+  pdl_launch_dependents();
+  pdl_wait();
 
   // The two control warps run their loops WARP-UNIFORMLY (all 32 lanes compute the same
   // addresses / descriptors, one elected lane executes the TMA / MMA / commit instructions).
@@ -589,8 +592,8 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
                                        cudaSharedmemCarveoutMaxShared));   // two CTAs per SM
     configured = true;
   }
-  flash_attn_kernel<<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(
-      tm, static_cast<__nv_bfloat16*>(out_bf16), cu_rows, n_heads, sl2);
+  VB_CHECK_CUDA(launch_pdl(flash_attn_kernel, grid, dim3(THREADS), SMEM_BYTES, static_cast<cudaStream_t>(stream), 1,
+                           tm, static_cast<__nv_bfloat16*>(out_bf16), cu_rows, n_heads, sl2));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

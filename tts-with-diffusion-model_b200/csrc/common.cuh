@@ -29,6 +29,42 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int num_sms();
 
+// Programmatic dependent launch (PDL), opt-in with VB200_PDL=1.  Every kernel of the denoise step
+// goes through launch_pdl() and brackets its first access to memory that an earlier kernel
+// produced (or still reads) with pdl_wait(), so that with the "programmatic stream serialization"
+// attribute its CTAs may become resident and run their prologue (barrier init, TMEM allocation,
+// tensor-map prefetch, reads of STATIC data such as weights or the batch layout) while the previous
+// kernel drains.  Valid under stream capture too.  Measured on B200 at batch 1 (89 kernels per
+// denoise step, graph replay): 0.878 ms with it, 0.861 ms without — the kernels of one step each
+// fill most SMs with CTAs of equal length, so there is no tail to overlap — hence off by default.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // Encodes a 2D row-major tensor map: dims {inner, outer}, box {box_inner, box_outer},
 // SWIZZLE_128B (box_inner * element size must be 128 bytes), zero fill / clipping out of bounds.
 int make_tmap_2d(CUtensorMap* out, vb200_dtype dtype, const void* gptr, uint64_t inner,
@@ -38,6 +74,12 @@ int cached_tmap(CUtensorMap* out, vb200_dtype dtype, const void* ptr, uint64_t i
                 uint64_t outer, uint64_t stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
 // ---------------------------------------------------------------- device PTX wrappers
+// PDL, device side: launch_dependents lets the next kernel's CTAs be scheduled as soon as this grid
+// leaves room; wait blocks until every kernel this one depends on has completed and flushed.  Both
+// are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 #ifdef __CUDACC__
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

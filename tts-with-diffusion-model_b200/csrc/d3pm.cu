@@ -167,6 +167,8 @@ __global__ void __launch_bounds__(256) posterior_sample_kernel(
     const int32_t* __restrict__ t_utt, const int32_t* __restrict__ utt,
     const float* __restrict__ table, int n_rows, int n_levels, int K, int S, int transition,
     const float* __restrict__ uniforms, uint32_t seed_lo, uint32_t seed_hi) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // everything below reads / writes activations
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tok = n_rows * n_levels;
@@ -354,6 +356,8 @@ __global__ void __launch_bounds__(256, 3) posterior_fast_kernel(
     const float* __restrict__ table, int n_rows, int n_levels, int S, int transition,
     uint32_t seed_lo, uint32_t seed_hi) {
   constexpr int K = KC * 256;
+  pdl_launch_dependents();
+  pdl_wait();                                   // everything below reads / writes activations
   constexpr int NR = KC * 8;                  // logits per lane
   constexpr float kLog2e = 1.4426950408889634f;
   constexpr unsigned kFull = 0xffffffffu;
@@ -567,13 +571,14 @@ static int launch_posterior(int32_t* x_out, float* post_out, const void* logits,
   const int cap = num_sms() * 8 * 4;
   if (grid > cap) grid = cap;
   const uint32_t lo = static_cast<uint32_t>(seed), hi = static_cast<uint32_t>(seed >> 32);
+  cudaError_t launch_rc = cudaSuccess;
   // production form: register-resident, single read of the logits (see posterior_fast_kernel)
   const bool aligned = (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
   if (!post_out && aligned && noise != VB200_NOISE_UNIFORMS && K % 256 == 0 && K <= 1024) {
     const T* lg = static_cast<const T*>(logits);
 #define VB_LAUNCH_F(KC, NZ)                                                                      \
-  posterior_fast_kernel<T, KC, NZ><<<grid, wpb * 32, 0, st>>>(x_out, lg, ld, x_t, row_utt, t_utt, \
-                                                             utt, table, n_rows, n_levels, S, tr, lo, hi)
+  launch_rc = launch_pdl(posterior_fast_kernel<T, KC, NZ>, dim3(grid), dim3(wpb * 32), 0, st, 1, x_out, lg, \
+                         static_cast<int64_t>(ld), x_t, row_utt, t_utt, utt, table, n_rows, n_levels, S, tr, lo, hi)
 #define VB_LAUNCH_FK(NZ)                                              \
   switch (K / 256) {                                                  \
     case 1: VB_LAUNCH_F(1, NZ); break;                                \
@@ -584,22 +589,26 @@ static int launch_posterior(int32_t* x_out, float* post_out, const void* logits,
     if (noise == VB200_NOISE_GREEDY) { VB_LAUNCH_FK(VB200_NOISE_GREEDY) } else { VB_LAUNCH_FK(VB200_NOISE_PHILOX) }
 #undef VB_LAUNCH_FK
 #undef VB_LAUNCH_F
+    VB_CHECK_CUDA(launch_rc);
     VB_CHECK_CUDA(cudaGetLastError());
     return VB200_OK;
   }
 #define VB_LAUNCH_P(NZ)                                                                        \
-  posterior_sample_kernel<T, NZ><<<grid, wpb * 32, 0, st>>>(                                   \
-      x_out, post_out, static_cast<const T*>(logits), ld, x_t, row_utt, t_utt, utt, table,     \
-      n_rows, n_levels, K, S, tr, uniforms, lo, hi)
+  launch_rc = launch_pdl(posterior_sample_kernel<T, NZ>, dim3(grid), dim3(wpb * 32), 0, st, 1, x_out, post_out,  \
+                         static_cast<const T*>(logits), static_cast<int64_t>(ld), x_t, row_utt, t_utt, utt, table, \
+                         n_rows, n_levels, K, S, tr, uniforms, lo, hi)
   if (noise == VB200_NOISE_PHILOX) VB_LAUNCH_P(VB200_NOISE_PHILOX);
   else if (noise == VB200_NOISE_UNIFORMS) VB_LAUNCH_P(VB200_NOISE_UNIFORMS);
   else VB_LAUNCH_P(VB200_NOISE_GREEDY);
 #undef VB_LAUNCH_P
+  VB_CHECK_CUDA(launch_rc);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
 
 __global__ void step_timesteps_kernel(int32_t* t_utt, int B, int delta) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // everything below reads / writes activations
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) t_utt[i] += delta;
 }
@@ -661,7 +670,8 @@ extern "C" int vb200_step_timesteps(int32_t* t_utt, int32_t B, int32_t delta,
                                     vb200_stream_t stream) {
   VB_REQUIRE(t_utt && B >= 0, "step_timesteps: bad arguments");
   if (B == 0) return VB200_OK;
-  step_timesteps_kernel<<<(B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(t_utt, B, delta);
+  VB_CHECK_CUDA(launch_pdl(step_timesteps_kernel, dim3((B + 127) / 128), dim3(128), 0,
+                           static_cast<cudaStream_t>(stream), 1, t_utt, B, delta));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

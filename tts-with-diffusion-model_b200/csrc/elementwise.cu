@@ -24,6 +24,8 @@ __global__ void __launch_bounds__(256) embed_gather_kernel(
     const int32_t* __restrict__ prom_ids, const int32_t* __restrict__ resp_ids,
     const int32_t* __restrict__ utt, const int32_t* __restrict__ row_utt,
     const int32_t* __restrict__ t_utt, int M, int d, int K, int resp_levels_in) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // everything below reads / writes activations
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < M; r += gridDim.x * wpb) {
@@ -78,6 +80,8 @@ __global__ void __launch_bounds__(256) norm_kernel(
     __nv_bfloat16* __restrict__ out, const float* __restrict__ x, const float* __restrict__ p0,
     const float* __restrict__ p1, const int32_t* __restrict__ level_utt,
     const int32_t* __restrict__ row_utt, int M, int d, float eps, float k, float c) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // everything below reads / writes activations
   constexpr int MAXV = 8;  // d <= 2048
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -153,6 +157,8 @@ __global__ void __launch_bounds__(256) adaln_rows_kernel(
     __nv_bfloat16* __restrict__ out, const float* __restrict__ x, const float* __restrict__ table,
     const int32_t* __restrict__ level_utt, const int32_t* __restrict__ row_utt, int M, int rows_per_warp,
     float eps, float k, float c) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // everything below reads / writes activations
   constexpr int d = NV * 256;
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -219,6 +225,8 @@ __global__ void __launch_bounds__(256) adaln_rows_kernel(
 __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(
     __nv_bfloat16* __restrict__ out, const float* __restrict__ x,
     const int32_t* __restrict__ row_index, int n_rows, int d) {
+  pdl_launch_dependents();
+  pdl_wait();                                   // everything below reads / writes activations
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += gridDim.x * wpb) {
@@ -259,11 +267,11 @@ extern "C" int vb200_embed_gather(float* x_out, const void* text_w, const void* 
   VB_REQUIRE(d > 0 && d % 8 == 0, "embed_gather: d=%d must be a positive multiple of 8", d);
   VB_REQUIRE(resp_levels_in >= 1 && resp_levels_in <= 8, "embed_gather: resp_levels_in=%d not in 1..8", resp_levels_in);
   if (M <= 0) return VB200_OK;
-  embed_gather_kernel<<<row_grid(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  VB_CHECK_CUDA(launch_pdl(embed_gather_kernel, dim3(row_grid(M, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
       x_out, static_cast<const __nv_bfloat16*>(text_w), static_cast<const __nv_bfloat16*>(prom_w),
       static_cast<const __nv_bfloat16*>(resp_w), static_cast<const __nv_bfloat16*>(sep),
       static_cast<const __nv_bfloat16*>(time_w), pe, text_ids, prom_ids, resp_ids, utt, row_utt,
-      t_utt, M, d, K, resp_levels_in);
+      t_utt, M, d, K, resp_levels_in));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
@@ -285,13 +293,14 @@ extern "C" int vb200_adaln(void* out_bf16, const float* x, const float* table,
     const int warps = (M + rpw - 1) / rpw;
     const int grid = (warps + 7) / 8;
     switch (d / 256) {
-      case 1: adaln_rows_kernel<1><<<grid, 256, 0, st>>>(o, x, table, level_utt, row_utt, M, rpw, eps, k, c); break;
-      case 2: adaln_rows_kernel<2><<<grid, 256, 0, st>>>(o, x, table, level_utt, row_utt, M, rpw, eps, k, c); break;
-      case 3: adaln_rows_kernel<3><<<grid, 256, 0, st>>>(o, x, table, level_utt, row_utt, M, rpw, eps, k, c); break;
-      default: adaln_rows_kernel<4><<<grid, 256, 0, st>>>(o, x, table, level_utt, row_utt, M, rpw, eps, k, c); break;
+      case 1: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<1>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c)); break;
+      case 2: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<2>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c)); break;
+      case 3: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<3>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c)); break;
+      default: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<4>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c)); break;
     }
   } else {
-    norm_kernel<0><<<row_grid(M, 8), 256, 0, st>>>(o, x, table, nullptr, level_utt, row_utt, M, d, eps, k, c);
+    VB_CHECK_CUDA(launch_pdl(norm_kernel<0>, dim3(row_grid(M, 8)), dim3(256), 0, st, 1, o, x, table,
+                             static_cast<const float*>(nullptr), level_utt, row_utt, M, d, eps, k, c));
   }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
@@ -304,8 +313,9 @@ extern "C" int vb200_layernorm(void* out_bf16, const float* x, const float* weig
   VB_REQUIRE(out_bf16 && x && weight && bias, "layernorm: null pointer");
   VB_REQUIRE(d > 0 && d % 8 == 0 && d <= 2048, "layernorm: d=%d must be a multiple of 8, <= 2048", d);
   if (M <= 0) return VB200_OK;
-  norm_kernel<1><<<row_grid(M, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(out_bf16), x, weight, bias, nullptr, nullptr, M, d, eps, 0.f, 0.f);
+  VB_CHECK_CUDA(launch_pdl(norm_kernel<1>, dim3(row_grid(M, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+      static_cast<__nv_bfloat16*>(out_bf16), x, weight, bias, static_cast<const int32_t*>(nullptr),
+      static_cast<const int32_t*>(nullptr), M, d, eps, 0.f, 0.f));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
@@ -316,8 +326,8 @@ extern "C" int vb200_gather_rows_bf16(void* out_bf16, const float* x, const int3
   VB_REQUIRE(out_bf16 && x && row_index, "gather_rows: null pointer");
   VB_REQUIRE(d > 0 && d % 8 == 0, "gather_rows: d=%d must be a multiple of 8", d);
   if (n_rows <= 0) return VB200_OK;
-  gather_rows_bf16_kernel<<<row_grid(n_rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(out_bf16), x, row_index, n_rows, d);
+  VB_CHECK_CUDA(launch_pdl(gather_rows_bf16_kernel, dim3(row_grid(n_rows, 8)), dim3(256), 0,
+                           static_cast<cudaStream_t>(stream), 1, static_cast<__nv_bfloat16*>(out_bf16), x, row_index, n_rows, d));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

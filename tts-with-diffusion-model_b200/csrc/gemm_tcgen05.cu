@@ -128,6 +128,10 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
   if (CTAS == 2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs initialised
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: the prologue above (barriers, TMEM, tensor-map prefetch) overlapped the previous kernel's
+  // tail; A, the residual stream and `out` may only be touched from here on.
+  pdl_launch_dependents();
+  pdl_wait();
 
   // Both control warps run their loops warp-uniformly (all lanes compute the same addresses, one
   // elected lane executes the TMA / MMA / commit instructions): issuing from a divergent
@@ -341,7 +345,7 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
       VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       configured = true;
     }
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(ta, tb, tout, bias, M, N, K);
+    VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K));
   } else if (ctas == 1) {
     auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 256>;
     static bool configured = false;
@@ -349,7 +353,7 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
       VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       configured = true;
     }
-    kern<<<grid, THREADS, SMEM_BYTES, st>>>(ta, tb, tout, bias, M, N, K);
+    VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K));
   } else {
     auto kern = gemm_tcgen05_kernel<EPI, OutT, 2, 256>;
     static bool configured = false;
@@ -357,19 +361,7 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
       VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       configured = true;
     }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    VB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, bias, M, N, K));
+    VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 2, ta, tb, tout, bias, M, N, K));
   }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
