@@ -285,8 +285,13 @@ def run_ours(args, wl):
     ses.x_t.fill_(model.mask_id)
     prof_steps = 2
     ses.t_utt.fill_(timesteps - 1)
+    K_cls = eng.w.n_out // 8
     for _ in range(prof_steps):
-        eng.forward(ses.lay, ses.ws, ses.x_t, ses.t_utt, use_time=True)
+        logits = eng.forward(ses.lay, ses.ws, ses.x_t, ses.t_utt, use_time=True)
+        ev = eng._prof_begin()
+        L.posterior_sample_from_logits(ses.x_t, None, logits, eng.w.n_out, ses.x_t, ses.lay.resp_row_utt, ses.t_utt,
+                                       ses.lay.utt, table, ses.lay.M_resp, 8, K_cls, tr, L.NOISE_PHILOX, None, args.seed)
+        eng._prof_end(ev, "posterior", ses.lay.M_resp * 8 * (2 * K_cls + 8))   # bytes: fp16 logits + x_t + x_out
     torch.cuda.synchronize(dev)
     prof, eng.profile = eng.profile, None
     agg = {}
@@ -315,6 +320,14 @@ def run_ours(args, wl):
                 "attention": {"kernel": "flash_attn_kernel", "achieved": attn_tf, "unit": "TFLOP/s",
                               "frac": attn_tf / peak_tf, "avg_launch_ms": at[1] / at[2],
                               "share_of_denoise_step": (at[1] / prof_steps) / step_total_ms}}
+    # the HBM-bound kernels of the step beside it (algorithmic bytes / launch time / measured copy bandwidth)
+    for kind, name in (("norm", "adaln_rows_kernel"), ("posterior", "posterior_fast_kernel")):
+        if kind in agg:
+            byt, t_ms, n = agg[kind]
+            gbs = byt / (t_ms * 1e-3) / 1e9
+            roofline[kind] = {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": peak_hbm, "unit": "GB/s",
+                              "frac": gbs / peak_hbm, "avg_launch_ms": t_ms / n,
+                              "share_of_denoise_step": (t_ms / prof_steps) / step_total_ms}
 
     # ---------------- p50 denoise-step latency (BASELINE.json's second metric): C2 shape, batch 1,
     # one CUDA-graph replay = denoiser forward + posterior + sample, >= 20 warm iterations

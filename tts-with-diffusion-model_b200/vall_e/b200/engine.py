@@ -237,10 +237,12 @@ class DenoiserEngine:
         self.profile.append((kind, flops, ev, end))
 
     def _norm(self, out, x, params, level_utt, lay):
+        ev = self._prof_begin()
         if self.w.norm_type == "adaln":
             L.adaln(out, x, params, level_utt, lay.row_utt)
         else:
             L.layernorm(out, x, params[0], params[1])
+        self._prof_end(ev, "norm", x.numel() * 6)      # bytes: fp32 in, bf16 out
 
     # ------------------------------------------------------------------ reverse loop
     def session(self, lay: BatchLayout) -> "Session":
