@@ -313,7 +313,10 @@ def run_ours(args, wl):
         traffic = tj.get("bytes_per_launch")
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (QKV/out/FFN1/FFN2/head launches)",
                 "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
-                "peak_source": f"{peak_src} bf16_tflops_sustained", "traffic": traffic,
+                "peak_source": f"{peak_src} bf16_tflops_sustained",
+                "peak_note": "cuBLAS bf16 back to back for 4 s at the pool's power cap; the launches here are timed one by "
+                             "one inside an eager pass of the step, so a lightly loaded box can exceed it (burst figure 1632)",
+                "traffic": traffic,
                 "traffic_note": "dram bytes of one FFN1 launch (largest GEMM) from profiles/r1_gemm_traffic.json; algorithmic 2.70 GB",
                 "avg_launch_ms": g[1] / g[2], "launches_timed": g[2],
                 "share_of_denoise_step": (g[1] / prof_steps) / step_total_ms,
