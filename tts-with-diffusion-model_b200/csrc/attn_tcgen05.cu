@@ -501,6 +501,22 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
     const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
     const int r_tile = quad * 32 + lane;               // query row inside the tile
     const uint32_t t_x = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    if (qt * BQ + quad * 32 >= T) {
+      // None of this warp's 32 query rows exists (ragged last tile: T = 1027 leaves 3 rows in the
+      // ninth tile).  Keep the barrier protocol going — whatever sits in its P columns only ever
+      // feeds its own, never stored, output rows — and leave the issue slots and the MUFU to the
+      // other CTA on this SM.
+      for (int j = 0; j < nblk; ++j) {
+        const int bf = j & 1;
+        mbar_wait(&s_full[bf], (j >> 1) & 1);
+        if (j > 0) {
+          mbar_wait(&pv_done[bf ^ 1], ((j - 1) >> 1) & 1);
+          if (lane == 0) mbar_arrive(&buf_free[bf ^ 1]);
+        }
+        if (lane == 0) mbar_arrive(&p_full[bf]);
+      }
+      mbar_wait(&pv_done[(nblk - 1) & 1], ((nblk - 1) >> 1) & 1);
+    } else {
     float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
     uint64_t o[32];                                    // 64 fp32 accumulators as f32x2 pairs
 #pragma unroll
@@ -554,6 +570,7 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
         *reinterpret_cast<uint4*>(o_dst + 2 * i) = pk;
       }
     }
+    }  // warp with valid rows
   }
 
   tc_fence_before();
