@@ -41,6 +41,14 @@ elif what == "gemm_big":     # FFN1 at the bench shape (256 utterances x 1027 ro
     out = torch.empty(M, 4096, dtype=torch.bfloat16, device=dev)
     for _ in range(3):
         L.gemm_bf16(out, A, W, bias, None, L.EPI_BIAS_GELU)
+elif what == "gemm_out":     # to_out at the bench shape: K = 1024, fp32 residual reduce-add epilogue
+    M = 262912
+    A = torch.randn(M, 1024, device=dev).bfloat16()
+    W = torch.randn(1024, 1024, device=dev).bfloat16()
+    bias = torch.randn(1024, device=dev)
+    x = torch.randn(M, 1024, device=dev)
+    for _ in range(3):
+        L.gemm_bf16(x, A, W, bias, x, L.EPI_BIAS_RESIDUAL)
 elif what == "posterior":
     sys.path.insert(0, str(ROOT / "tts-with-diffusion-model_b200"))
     from vall_e.vall_e import d3pm
