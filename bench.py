@@ -38,6 +38,7 @@ WORKLOADS = {
     "c2": (1, 50, 225, 750, 51, "absorbing"),
     "c3": (256, 50, 225, 750, 51, "absorbing"),
     "c4": (16, 50, 225, 2250, 51, "absorbing"),
+    "c5": (64, 50, 225, 300, 26, "uniform"),      # BASELINE configs[4], one point of its sweep: S = 25, uniform
 }
 MODEL = dict(n_tokens=1024, d_model=1024, n_heads=16, n_layers=12)
 METRIC, UNIT = "codec_tokens_per_sec", "tokens/s"
