@@ -171,11 +171,15 @@ int vb200_posterior_sample_from_logits(int32_t* x_out, float* post_out, const vo
                                        vb200_stream_t stream);
 
 /* H1 + P in one call (reference base.py:355,440 followed by
- * ar_discrete.py:347-375,401-420): logits = head_in (n_rows, d) bf16 x W (n_levels*K, d)^T + bias,
- * written to the caller's scratch `logits` (n_rows, n_levels*K) of logits_dtype, then the reverse
- * step of vb200_posterior_sample_from_logits on them, both stream-ordered.  Two launches: a
- * single-kernel epilogue fusion was analysed and rejected (the two-pass recompute
- * costs more tensor time than the logits round trip it saves). */
+ * ar_discrete.py:347-375,401-420): logits = head_in (n_rows, d) bf16 x W (n_levels*K, d)^T + bias and
+ * the reverse step of vb200_posterior_sample_from_logits on them.
+ * For K % 256 == 0 and noise != VB200_NOISE_UNIFORMS this is ONE kernel: the reverse step runs as
+ * the GEMM's epilogue (streaming reservoir sampling over the column tiles of a level, see
+ * csrc/head_sample_tcgen05.cu) and `logits` is not touched.  Otherwise (arbitrary K, supplied
+ * uniforms, or VB200_FUSED_HEAD=0) the logits go through the caller's scratch `logits`
+ * (n_rows, n_levels*K) of logits_dtype and the standalone kernel.  The Philox draws of the two forms
+ * differ (both are exact samples of the same posterior); greedy codes agree up to the fp16
+ * rounding of the unfused logits. */
 int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_dtype logits_dtype,
                                 const void* head_in_bf16, const void* W_bf16, const float* bias,
                                 int32_t n_rows, int32_t d, int32_t n_levels, int32_t K,

@@ -74,8 +74,35 @@ def small_kernels():
         print(f"posterior[{name}] tokens={rows*8}: {ms:.3f} ms {rows*8*(2*K+8)/ms/1e6:.0f} GB/s", flush=True)
 
 
+def head():
+    """classifier + reverse step through vb200_head_posterior_sample (fused unless VB200_FUSED_HEAD=0)"""
+    import os
+    sys.path.insert(0, str(ROOT / "tts-with-diffusion-model_b200"))
+    from vall_e.vall_e import d3pm
+    S, K, d = 51, 1024, 1024
+    tab = d3pm.scalar_table(S, K, "absorbing").to(dev)
+    W = (torch.randn(8 * K, d, device=dev) * 0.03).bfloat16()
+    bias = torch.randn(8 * K, device=dev)
+    for B in (256, 1):
+        rows = 750 * B
+        head_in = torch.randn(rows, d, device=dev).bfloat16()
+        scratch = torch.empty(rows, 8 * K, dtype=torch.float16, device=dev)
+        x_t = torch.full((rows, 8), K // 2, dtype=torch.int32, device=dev)
+        row_utt = torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(750)
+        utt = torch.zeros(B, L.U_STRIDE, dtype=torch.int32, device=dev)
+        utt[:, L.U_RESP0] = torch.arange(B, device=dev, dtype=torch.int32) * 750
+        t_utt = torch.full((B,), 30, dtype=torch.int32, device=dev)
+        o = torch.empty(rows, 8, dtype=torch.int32, device=dev)
+        ms = timeit(lambda: L.head_posterior_sample(o, scratch, head_in, W, bias, x_t, row_utt, t_utt, utt, tab, 8, K,
+                                                    L.ABSORBING, L.NOISE_PHILOX, seed=1), iters=10)
+        print(f"head+posterior[fused={os.environ.get('VB200_FUSED_HEAD', '1')}] rows={rows}: {ms:.3f} ms "
+              f"({2*rows*8*K*d/ms/1e9:.0f} TFLOP/s of GEMM work)", flush=True)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what == "head":
+        head()
     if what in ("all", "small"):
         small_kernels()
     if what in ("all", "gemm"):

@@ -17,7 +17,7 @@ CSRC = HERE / "csrc"
 OUT_DIR = HERE / "vall_e" / "b200"
 LIB = OUT_DIR / "libvalle_b200.so"
 OBJ_DIR = HERE / "build" / "obj"
-SOURCES = ["api.cu", "elementwise.cu", "d3pm.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "debug_simt.cu"]
+SOURCES = ["api.cu", "elementwise.cu", "d3pm.cu", "gemm_tcgen05.cu", "attn_tcgen05.cu", "head_sample_tcgen05.cu", "debug_simt.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

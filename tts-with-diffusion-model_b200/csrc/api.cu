@@ -166,6 +166,21 @@ extern "C" int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_d
                                            const int32_t* utt, const float* table, int32_t S,
                                            vb200_transition tr, vb200_noise noise, const float* uniforms,
                                            uint64_t seed, vb200_stream_t stream) {
+  // fused form: the reverse step runs as the GEMM's epilogue and `logits` stays untouched
+  static int fused = -1;
+  if (fused < 0) {
+    const char* e = getenv("VB200_FUSED_HEAD");
+    fused = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (fused && n_rows > 0 && vb200::head_sample_supported(d, K, static_cast<int>(noise))) {
+    if (!(x_out && head_in_bf16 && W_bf16 && bias && x_t && row_utt && t_utt && utt && table)) {
+      vb200::set_error("head_posterior_sample: null pointer");
+      return VB200_ERR_INVALID;
+    }
+    return vb200::head_sample_fused(x_out, head_in_bf16, W_bf16, bias, x_t, row_utt, t_utt, utt, table, n_rows, d,
+                             n_levels, K, S, static_cast<int>(tr), static_cast<int>(noise), seed,
+                             static_cast<cudaStream_t>(stream));
+  }
   const int rc = vb200_gemm_bf16(logits, logits_dtype, head_in_bf16, W_bf16, bias, nullptr, n_rows,
                                  n_levels * K, d, VB200_EPI_BIAS, stream);
   if (rc != VB200_OK) return rc;

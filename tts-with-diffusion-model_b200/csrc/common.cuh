@@ -29,6 +29,13 @@ int cuda_fail(cudaError_t e, const char* what);
 
 int num_sms();
 
+// classifier GEMM with the reverse step as its epilogue (head_sample_tcgen05.cu)
+bool head_sample_supported(int d, int K, int noise);
+int head_sample_fused(int32_t* x_out, const void* head_in, const void* W, const float* bias, const int32_t* x_t,
+                      const int32_t* row_utt, const int32_t* t_utt, const int32_t* utt, const float* table,
+                      int n_rows, int d, int n_levels, int K, int S, int tr, int noise, uint64_t seed,
+                      cudaStream_t st);
+
 // Programmatic dependent launch (PDL), opt-in with VB200_PDL=1.  Every kernel of the denoise step
 // goes through launch_pdl() and brackets its first access to memory that an earlier kernel
 // produced (or still reads) with pdl_wait(), so that with the "programmatic stream serialization"
@@ -376,6 +383,34 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+constexpr float kEps = 1.0e-6f;          // ar_discrete.py:276
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct Philox {
+  uint32_t k0, k1;
+  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
+    uint32_t a = k0, b = k1;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      c0 = hi1 ^ c1 ^ a;
+      c1 = lo1;
+      c2 = hi0 ^ c3 ^ b;
+      c3 = lo0;
+      a += 0x9E3779B9u;
+      b += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+  }
+};
+__device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * 5.9604644775390625e-8f; }
+__device__ __forceinline__ float exp2f_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

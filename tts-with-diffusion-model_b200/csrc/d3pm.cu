@@ -5,34 +5,7 @@
 
 namespace vb200 {
 
-constexpr float kEps = 1.0e-6f;          // ar_discrete.py:276
 constexpr float kTiny = 1.17549435e-38f; // torch.finfo(float32).tiny, ar_discrete.py:414,485
-
-// ---------------------------------------------------------------- Philox4x32-10
-struct Philox {
-  uint32_t k0, k1;
-  __device__ __forceinline__ uint4 operator()(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) const {
-    uint32_t a = k0, b = k1;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-      c0 = hi1 ^ c1 ^ a;
-      c1 = lo1;
-      c2 = hi0 ^ c3 ^ b;
-      c3 = lo0;
-      a += 0x9E3779B9u;
-      b += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-  }
-};
-__device__ __forceinline__ float u01(uint32_t x) { return (x >> 8) * 5.9604644775390625e-8f; }
-__device__ __forceinline__ float exp2f_fast(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 // Gumbel noise exactly as the reference forms it, evaluated through double so that each fp32
 // log is correctly rounded (the CPU reference's SLEEF logf is <= 1 ulp; agreeing with the
