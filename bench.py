@@ -288,11 +288,12 @@ def run_ours(args, wl):
     ses.t_utt.fill_(timesteps - 1)
     K_cls = eng.w.n_out // 8
     for _ in range(prof_steps):
-        logits = eng.forward(ses.lay, ses.ws, ses.x_t, ses.t_utt, use_time=True)
+        head_in = eng.forward(ses.lay, ses.ws, ses.x_t, ses.t_utt, use_time=True, head=False)
         ev = eng._prof_begin()
-        L.posterior_sample_from_logits(ses.x_t, None, logits, eng.w.n_out, ses.x_t, ses.lay.resp_row_utt, ses.t_utt,
-                                       ses.lay.utt, table, ses.lay.M_resp, 8, K_cls, tr, L.NOISE_PHILOX, None, args.seed)
-        eng._prof_end(ev, "posterior", ses.lay.M_resp * 8 * (2 * K_cls + 8))   # bytes: fp16 logits + x_t + x_out
+        L.head_posterior_sample(ses.x_t, ses.ws.logits, head_in, eng.w.w_cls, eng.w.b_cls, ses.x_t,
+                                ses.lay.resp_row_utt, ses.t_utt, ses.lay.utt, table, 8, K_cls, tr, L.NOISE_PHILOX,
+                                None, args.seed)
+        eng._prof_end(ev, "head_sample", 2 * ses.lay.M_resp * eng.w.n_out * eng.w.d)
     torch.cuda.synchronize(dev)
     prof, eng.profile = eng.profile, None
     agg = {}
@@ -302,7 +303,10 @@ def run_ours(args, wl):
         a[1] += s.elapsed_time(e)
         a[2] += 1
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    g = agg.get("gemm", [0.0, 1.0, 1])
+    g = list(agg.get("gemm", [0.0, 1.0, 1]))
+    hsamp = agg.get("head_sample")
+    if hsamp:                 # the classifier GEMM (with the reverse step as its epilogue) is a tcgen05 GEMM too
+        g = [g[0] + hsamp[0], g[1] + hsamp[1], g[2] + hsamp[2]]
     at = agg.get("attn", [0.0, 1.0, 1])
     gemm_tf = g[0] / (g[1] * 1e-3) / 1e12
     attn_tf = at[0] / (at[1] * 1e-3) / 1e12
@@ -312,7 +316,7 @@ def run_ours(args, wl):
     if tf.exists():
         tj = json.loads(tf.read_text())
         traffic = tj.get("bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (QKV/out/FFN1/FFN2/head launches)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (QKV/out/FFN1/FFN2) + head_sample_kernel (classifier)",
                 "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
                 "peak_source": f"{peak_src} bf16_tflops_sustained",
                 "peak_note": "cuBLAS bf16 back to back for 4 s at the pool's power cap; the launches here are timed one by "
@@ -325,7 +329,13 @@ def run_ours(args, wl):
                               "frac": attn_tf / peak_tf, "avg_launch_ms": at[1] / at[2],
                               "share_of_denoise_step": (at[1] / prof_steps) / step_total_ms}}
     # the HBM-bound kernels of the step beside it (algorithmic bytes / launch time / measured copy bandwidth)
-    for kind, name in (("norm", "adaln_rows_kernel"), ("posterior", "posterior_fast_kernel")):
+    if hsamp:
+        roofline["head_sample"] = {"kernel": "head_sample_kernel (classifier GEMM + D3PM reverse step, one launch)",
+                                   "bound": "tensor", "achieved": hsamp[0] / (hsamp[1] * 1e-3) / 1e12,
+                                   "unit": "TFLOP/s", "frac": hsamp[0] / (hsamp[1] * 1e-3) / 1e12 / peak_tf,
+                                   "avg_launch_ms": hsamp[1] / hsamp[2],
+                                   "share_of_denoise_step": (hsamp[1] / prof_steps) / step_total_ms}
+    for kind, name in (("norm", "adaln_rows_kernel"),):
         if kind in agg:
             byt, t_ms, n = agg[kind]
             gbs = byt / (t_ms * 1e-3) / 1e9

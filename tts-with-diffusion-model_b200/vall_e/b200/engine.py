@@ -311,7 +311,7 @@ class Session:
                 head_in = eng.forward(lay, ws, x_t, t_utt, use_time=True, head=False)
                 L.head_posterior_sample(x_t, ws.logits, head_in, w.w_cls, w.b_cls, x_t, lay.resp_row_utt, t_utt,
                                         lay.utt, table, n_levels, K, transition, noise, uniforms, seed)
-                eng.launches += 1
+                eng.launches += 0 if L.head_fused(w.d, K, noise) else 1   # the `+= 2` below counts one of them
             else:                 # per-launch timing hooks / CUDA-core validation path: separate calls
                 logits = eng.forward(lay, ws, x_t, t_utt, use_time=True)
                 L.posterior_sample_from_logits(x_t, None, logits, w.n_out, x_t, lay.resp_row_utt, t_utt, lay.utt,

@@ -173,6 +173,13 @@ def head_posterior_sample(x_out, logits, head_in, W, bias, x_t, row_utt, t_utt, 
         noise, ptr(uniforms), seed, stream()), "vb200_head_posterior_sample")
 
 
+def head_fused(d, K, noise) -> bool:
+    """Mirrors head_sample_supported() in csrc/head_sample_tcgen05.cu: one kernel or two."""
+    import os
+    return (os.environ.get("VB200_FUSED_HEAD", "1")[:1] != "0" and K % 256 == 0 and 256 <= K <= 4096
+            and d % 8 == 0 and noise != NOISE_UNIFORMS)
+
+
 WS_FIELDS = ("x", "h", "qkv", "att", "ff", "head_in", "logits")
 
 
