@@ -41,6 +41,25 @@ __global__ void kern(float* out, long long* cyc, int iters, float a, float b) {
     } else if (OP == 5) {      // fadd scalar
 #pragma unroll
       for (int i = 0; i < 16; ++i) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(v[i]) : "f"(a));
+    } else if (OP == 7) {      // packed half exponentials: 8 instructions = 16 results
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t* h = reinterpret_cast<uint32_t*>(&v[i]);
+        asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(*h));
+      }
+    } else if (OP == 8) {      // f32 pair -> f16x2 pack
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t p;
+        asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(p) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+        v[2 * i] = __uint_as_float(p);
+      }
+    } else if (OP == 9) {      // half2 add
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        uint32_t* h = reinterpret_cast<uint32_t*>(&v[i]);
+        asm volatile("add.rn.f16x2 %0, %0, %1;" : "+r"(*h) : "r"(0x3c003c00u));
+      }
     } else if (OP == 6) {      // mixed: per 4 floats  1 FFMA2x2 + MUFU x3 ... the real ratio: see attn kernel
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -83,5 +102,8 @@ int main() {
   run<4>("F2FP.BF16 pack", 8, o, c);
   run<5>("FADD", 16, o, c);
   run<6>("FFMA2 + MUFU.EX2 pair", 16, o, c);
+  run<7>("MUFU.EX2 f16x2", 8, o, c);
+  run<8>("F2FP.F16 pack", 8, o, c);
+  run<9>("HADD2", 16, o, c);
   return 0;
 }

@@ -62,28 +62,6 @@ __device__ __forceinline__ void tmem_ld_32x32p(uint32_t taddr, uint32_t (&r)[32]
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x32p(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
-      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]),
-      "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
-      "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
-      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
-      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -91,21 +69,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 
-// exp2 on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + r with the 1.5 * 2^23
-// magic constant, 2^r by a cubic on [-0.5, 0.5] (|rel err| < 7.5e-5, far below the bf16 rounding
-// of P), exponent patched in with an integer add.  MUFU.EX2 runs at 16 lanes / clk / SM on B200
-// (tools/mufu_bench.cu), which makes a 128x128 softmax block MUFU-bound at about twice the time of
-// its MMAs; moving a share of the exponentials here rebalances the two pipes (the FA4 trick).
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float t = x + 12582912.0f;
-  const float r = x - (t - 12582912.0f);
-  float p = fmaf(r, 0.05517167f, 0.24261113f);     // minimax cubic of 2^r on [-0.5, 0.5]
-  p = fmaf(r, p, 0.69326097f);
-  p = fmaf(r, p, 0.99992806f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-// two exponentials at once on the FMA / ALU pipes (same cubic as ex2_poly)
+// exp2 on the FMA / ALU pipes (no MUFU), two at once with packed f32x2 arithmetic: round-to-nearest
+// split x = n + r with the 1.5 * 2^23 magic constant, 2^r by a minimax cubic on [-0.5, 0.5]
+// (|rel err| < 7.5e-5, far below the bf16 rounding of P), exponent patched in with an integer add.
+// MUFU.EX2 runs at 16 lanes / clk / SM on B200 (tools/mufu_bench.cu; the f16x2 form is two MUFU
+// operations, no faster), which makes the softmax of a 128x128 block co-limited by MUFU and
+// instruction issue; moving a share of the exponentials here rebalances the two (the FA4 trick).
 __device__ __forceinline__ void ex2_poly2(uint64_t x, float& p0, float& p1) {
   float x0, x1;
   unpack2(x, x0, x1);
@@ -532,17 +501,8 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
       uint64_t* pvd = &pv_done[bf ^ 1];
       uint64_t* bfr = &buf_free[bf ^ 1];
       const uint32_t pv_par = ((j - 1) >> 1) & 1;
-#if defined(VB200_ATTN_NOSOFTMAX)   // timing experiment: barrier traffic only
-      if (j > 0) { mbar_wait(pvd, pv_par); tc_fence_after(); tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(bfr); }
-      l = 1.f; (void)n_chunks; (void)t_buf; (void)t_prev; (void)m;
-#else
-#if defined(VB200_ATTN_CHUNK32)
-      if (!tail) softmax_block<false>(t_buf, t_prev, pvd, pv_par, bfr, lane, j, 4, BKV, scale_log2, m, l, alpha_prev, o);
-#else
       if (!tail) softmax_block_full(t_buf, t_prev, pvd, pv_par, bfr, lane, j, scale_log2, m, l, alpha_prev, o);
-#endif
       else softmax_block<true>(t_buf, t_prev, pvd, pv_par, bfr, lane, j, n_chunks, last_valid, scale_log2, m, l, alpha_prev, o);
-#endif
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();

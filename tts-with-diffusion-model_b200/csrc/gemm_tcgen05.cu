@@ -43,25 +43,13 @@ constexpr int SMEM_BYTES = 4 * 48 * 1024 + EPI_WARPS * EPI_TILE_BYTES + 1024 /*a
 constexpr uint32_t TMEM_COLS = 512;
 }  // namespace gemm
 
-__device__ __forceinline__ float gelu_erf_fast(float x) {
-  // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) = relu(x) - |x| q(z),  q(z) = 0.5 erfc(z),  z = |x| / sqrt 2.
-  // log2 q(z) is smooth: a degree-6 minimax polynomial on [0, 6] gives |gelu error| < 4.5e-5 for all x
-  // (beyond z = 6, i.e. |x| > 8.5, q < 1e-17).  12 instructions, one MUFU (ex2).
-  const float z = fminf(fabsf(x) * 0.70710678118654752f, 6.0f);
-  float p = fmaf(z, 9.22344479e-05f, -2.20238999e-03f);
-  p = fmaf(z, p, 2.23510694e-02f);
-  p = fmaf(z, p, -1.29628107e-01f);
-  p = fmaf(z, p, -9.38564420e-01f);
-  p = fmaf(z, p, -1.62045550e+00f);
-  p = fmaf(z, p, -1.00044155e+00f);
-  float q;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(p));
-  return fmaxf(x, 0.0f) - fabsf(x * q);
-}
-
-// Two at once with packed f32x2 arithmetic (FFMA2: half the issue slots of the polynomial), written
-// as gelu(x) = x * (0.5 + copysign(0.5 - q, x)) — the same q as above.  With the scalar form the
-// epilogue of the FFN1 GEMM (K = 1024) took longer than the tile's MMAs (tensor pipe 86 % active).
+// gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) = x * (x > 0 ? 1 - q : q),  q(z) = 0.5 erfc(z),  z = |x| / sqrt 2.
+// log2 q(z) is smooth: a degree-6 minimax polynomial on [0, 6] gives |gelu error| < 4.5e-5 for all x
+// (beyond z = 6, i.e. |x| > 8.5, q < 1e-17); one MUFU (ex2) per element.
+// Two elements at once with packed f32x2 arithmetic (FFMA2: half the issue slots of the polynomial),
+// written as gelu(x) = x * (0.5 + copysign(0.5 - q, x)).  With a scalar form (12 instructions per
+// element) the epilogue of the FFN1 GEMM (K = 1024) took longer than the tile's MMAs (tensor pipe
+// 86 % active).
 __device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
   const float z0 = fminf(fabsf(x0) * 0.70710678118654752f, 6.0f);
   const float z1 = fminf(fabsf(x1) * 0.70710678118654752f, 6.0f);
