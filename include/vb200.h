@@ -152,6 +152,13 @@ int vb200_q_sample(int32_t* x_out, const int32_t* x0, const int32_t* t_tok, cons
                    const float* uniforms, const float* table, int32_t n_tok, int32_t K,
                    int32_t S, vb200_transition tr, vb200_stream_t stream);
 
+/* q_sample with in-kernel noise (training forwards, ar_discrete.py:651-653): the same categorical
+ * law — weights exp(fp16 log(Qbar_t[x0, j] + eps)) — drawn in O(1) per token from one Philox
+ * uniform keyed by (seed, token index, t) instead of K Gumbel variates shipped from the host. */
+int vb200_q_sample_philox(int32_t* x_out, const int32_t* x0, const int32_t* t_tok, const int32_t* mask,
+                          const float* table, int32_t n_tok, int32_t K, int32_t S,
+                          vb200_transition tr, uint64_t seed, vb200_stream_t stream);
+
 /* P (standalone logits-in form): q_posterior_logits + p_sample (ar_discrete.py:347-375,401-420)
  * in closed form, O(K) per token, fp32 in registers:
  *   out_j = log(f1_j + eps) + log(f2_j + eps),  f1_j = Q_t[j, x_t],
@@ -187,6 +194,14 @@ int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_dtype logits
                                 const int32_t* utt, const float* table, int32_t S,
                                 vb200_transition tr, vb200_noise noise, const float* uniforms,
                                 uint64_t seed, vb200_stream_t stream);
+
+/* Training forward's loss (reference ar_discrete.py:684-687 `F.cross_entropy` on the
+ * classifier output): loss[r, l] = -log softmax(head_in[r] W_l^T + b_l)[targets[r, l]], float32
+ * (n_rows, n_levels), computed as the classifier GEMM's epilogue (online log-sum-exp over the column
+ * tiles of a level; no logits in HBM).  Needs K % 256 == 0. */
+int vb200_head_ce_loss(float* loss, const void* head_in_bf16, const void* W_bf16, const float* bias,
+                       const int32_t* targets, int32_t n_rows, int32_t d, int32_t n_levels, int32_t K,
+                       vb200_stream_t stream);
 
 /* Scratch the caller provides for one denoiser forward over M packed rows, M_resp of them response
  * rows (the library never allocates; reference: the activations of Base.forward base.py:427-443).

@@ -1,5 +1,7 @@
 """GPU parity tests, model level: denoiser logits, NAR pass and the D3PM reverse loop through the
 reference-facing API (lists of per-utterance tensors) against the oracle and the golden fixtures."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -306,3 +308,56 @@ def test_full_size_model_size_independent_properties():
         assert torch.equal(solo[0], a[i]), i
     rev = m.generate_audio(text[::-1], proms[::-1], resp_lens=resp[::-1], seed=11, gids=[2, 1, 0])
     assert all(torch.equal(x, y) for x, y in zip(rev[::-1], a))            # batch order does not matter
+
+
+def test_training_forward_loss_vs_oracle_and_torch():
+    """q_sample with in-kernel noise + cross-entropy as the classifier GEMM's epilogue.
+    (a) the loss of Diffusion.d3pm_loss equals the cross-entropy of the ORACLE's logits on the same
+    x_t (tolerance: the 2e-2 logits bar); (b) the fused per-token losses equal torch's CE on this
+    library's own logits; (c) the O(1) Philox q_sample follows the table's categorical law."""
+    from oracle import denoiser as on
+    from vall_e.b200 import lib as L
+    from vall_e.vall_e import d3pm as pd
+    K, d, h, nl, S = 256, 128, 2, 2, 12
+    m, sd = _make(K, d, h, nl, S, "absorbing", seed=31)
+    lens = [(5, 9, 33), (7, 4, 70)]
+    text, proms, x0 = _batch(K, lens, 5)
+    dtext, dproms, dx0 = [x.to(DEV) for x in text], [x.to(DEV) for x in proms], [x.to(DEV) for x in x0]
+    t = torch.tensor([4, 9])
+    total, per_tok, x_t = m.d3pm_loss(dtext, dproms, dx0, t, seed=3, return_per_token=True)
+    xt_list = [r.cpu().long() for r in x_t.split([c for _, _, c in lens])]
+    ref_logits = on.diffusion_logits(sd, text, proms, xt_list, t, h, nl)
+    ce = []
+    for lg, tgt in zip(ref_logits, x0):
+        lg = torch.as_tensor(lg).double().reshape(len(tgt), 8, K)
+        ce.append(torch.nn.functional.cross_entropy(lg.reshape(-1, K), tgt.reshape(-1), reduction="none"))
+    ce = torch.cat(ce)
+    assert abs(total.item() - ce.mean().item()) < 2e-2, (total.item(), ce.mean().item())
+    assert (per_tok.cpu().double().view(-1) - ce).abs().max().item() < 6e-2
+    # (b) against torch on this library's own fp32 logits
+    own = m.denoise_logits(dtext, dproms, [x.to(DEV) for x in xt_list], t)
+    own_ce = torch.cat([torch.nn.functional.cross_entropy(lg.reshape(-1, K).float(), tgt.to(DEV).reshape(-1),
+                                                          reduction="none") for lg, tgt in zip(own, x0)])
+    assert (per_tok.view(-1) - own_ce).abs().max().item() < 2e-3
+    # sweep form runs and is reproducible
+    a = m.d3pm_loss(dtext, dproms, dx0, None, seed=1)
+    b = m.d3pm_loss(dtext, dproms, dx0, None, seed=1)
+    assert torch.equal(a, b) and math.isfinite(a.item())
+    # (c) law of the Philox q_sample: absorbing, x0 != m
+    n, t0 = 200000, 7
+    table = pd.scalar_table(S + 1, K, "absorbing").to(DEV)
+    x0v = torch.full((n,), 5, dtype=torch.int32, device=DEV)
+    tt = torch.full((n,), t0, dtype=torch.int32, device=DEV)
+    out = torch.empty_like(x0v)
+    L.q_sample_philox(out, x0v, tt, None, table, K, L.ABSORBING, seed=9)
+    row = table[t0].cpu().double()
+    w = torch.full((K,), math.exp(row[L.TAB_LOG_OFF].item()), dtype=torch.float64)
+    w[5], w[K // 2] = math.exp(row[L.TAB_LOG_KEEP].item()), math.exp(row[L.TAB_LOG_ABSORB].item())
+    p = w / w.sum()
+    counts = torch.bincount(out.cpu().long(), minlength=K).double()
+    for j in (5, K // 2):
+        exp_j = p[j].item() * n
+        assert abs(counts[j].item() - exp_j) < 6 * math.sqrt(exp_j * (1 - p[j].item())) + 1, (j, counts[j].item(), exp_j)
+    rest_exp = n - (p[5] + p[K // 2]).item() * n
+    rest_obs = n - counts[5].item() - counts[K // 2].item()
+    assert abs(rest_obs - rest_exp) < 6 * math.sqrt(max(rest_exp, 1.0)) + 1

@@ -188,3 +188,20 @@ extern "C" int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_d
                                             static_cast<int64_t>(n_levels) * K, x_t, row_utt, t_utt, utt,
                                             table, n_rows, n_levels, K, S, tr, noise, uniforms, seed, stream);
 }
+
+extern "C" int vb200_head_ce_loss(float* loss, const void* head_in_bf16, const void* W_bf16, const float* bias,
+                                  const int32_t* targets, int32_t n_rows, int32_t d, int32_t n_levels, int32_t K,
+                                  vb200_stream_t stream) {
+  if (n_rows == 0) return VB200_OK;
+  if (!(loss && head_in_bf16 && W_bf16 && bias && targets)) {
+    vb200::set_error("head_ce_loss: null pointer");
+    return VB200_ERR_INVALID;
+  }
+  if (n_rows < 0 || n_levels < 1 || d <= 0 || d % 8 != 0 || K < 256 || K % 256 != 0) {
+    vb200::set_error("head_ce_loss: needs d %% 8 == 0 and K a multiple of 256 (n_rows=%d d=%d n_levels=%d K=%d)",
+                     n_rows, d, n_levels, K);
+    return VB200_ERR_UNSUPPORTED;
+  }
+  return vb200::head_ce_fused(loss, head_in_bf16, W_bf16, bias, targets, n_rows, d, n_levels, K,
+                              static_cast<cudaStream_t>(stream));
+}

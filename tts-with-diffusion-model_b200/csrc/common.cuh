@@ -35,6 +35,8 @@ int head_sample_fused(int32_t* x_out, const void* head_in, const void* W, const 
                       const int32_t* row_utt, const int32_t* t_utt, const int32_t* utt, const float* table,
                       int n_rows, int d, int n_levels, int K, int S, int tr, int noise, uint64_t seed,
                       cudaStream_t st);
+int head_ce_fused(float* loss_out, const void* head_in, const void* W, const float* bias, const int32_t* targets,
+                  int n_rows, int d, int n_levels, int K, cudaStream_t st);
 
 // Programmatic dependent launch (PDL), opt-in with VB200_PDL=1.  Every kernel of the denoise step
 // goes through launch_pdl() and brackets its first access to memory that an earlier kernel

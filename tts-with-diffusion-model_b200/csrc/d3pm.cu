@@ -71,6 +71,48 @@ __global__ void __launch_bounds__(256) q_sample_kernel(
   }
 }
 
+// q_sample with in-kernel noise: the same categorical law as above — weights exp(fp16 log(Qbar_t[x0, j]
+// + eps)), read from the table — drawn in O(1) from one Philox uniform per token instead of an
+// argmax over K Gumbel variates: only the classes x0 and m carry their own weight, all others share
+// one (the eps leak), so the CDF has three pieces.  For training forwards (ar_discrete.py:651-653),
+// where the reference draws K uniforms per token on the CPU and ships them to the device.
+__global__ void __launch_bounds__(256) q_sample_philox_kernel(
+    int32_t* __restrict__ x_out, const int32_t* __restrict__ x0, const int32_t* __restrict__ t_tok,
+    const int32_t* __restrict__ mask, const float* __restrict__ table, int n_tok, int K, int S,
+    int transition, uint32_t seed_lo, uint32_t seed_hi) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const Philox ph{seed_lo, seed_hi};
+  for (int tok = blockIdx.x * blockDim.x + threadIdx.x; tok < n_tok; tok += gridDim.x * blockDim.x) {
+    const int x = x0[tok];
+    const int t = min(max(t_tok[tok], 0), S - 1);
+    const float* tab = table + static_cast<size_t>(t) * VB200_TAB_STRIDE;
+    const bool absorbing = transition == VB200_ABSORBING;
+    const int m = absorbing ? K / 2 : -1;
+    const float w_off = __expf(tab[VB200_TAB_LOG_OFF]);
+    float w_self, w_m = 0.f;
+    int n_other;
+    if (absorbing && x == m) { w_self = __expf(tab[VB200_TAB_LOG_BOTH]); n_other = K - 1; }
+    else if (absorbing) { w_self = __expf(tab[VB200_TAB_LOG_KEEP]); w_m = __expf(tab[VB200_TAB_LOG_ABSORB]); n_other = K - 2; }
+    else { w_self = __expf(tab[VB200_TAB_LOG_KEEP]); n_other = K - 1; }
+    const uint4 r = ph(0x0D3B0000u, static_cast<uint32_t>(tok), 0u, static_cast<uint32_t>(t));
+    const float target = u01(r.x) * (w_self + w_m + n_other * w_off);
+    int pick;
+    if (target < w_self) {
+      pick = x;
+    } else if (target < w_self + w_m) {
+      pick = m;
+    } else {                                              // one of the other classes, uniformly
+      int j = min(static_cast<int>(u01(r.y) * n_other), n_other - 1);
+      const int lo = (w_m > 0.f) ? min(x, m) : x, hi = (w_m > 0.f) ? max(x, m) : -1;
+      if (j >= lo) ++j;                                   // skip x (and m), in ascending order
+      if (hi >= 0 && j >= hi) ++j;
+      pick = j;
+    }
+    x_out[tok] = pick * (mask ? mask[tok] : 1);
+  }
+}
+
 // ---------------------------------------------------------------- P: posterior + sample
 template <typename T>
 __device__ __forceinline__ float load_logit(const T* p, int j);
@@ -604,6 +646,22 @@ extern "C" int vb200_q_sample(int32_t* x_out, const int32_t* x0, const int32_t* 
   if (grid > cap) grid = cap;
   q_sample_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
       x_out, x0, t_tok, mask, uniforms, table, n_tok, K, S, static_cast<int>(tr));
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
+}
+
+extern "C" int vb200_q_sample_philox(int32_t* x_out, const int32_t* x0, const int32_t* t_tok,
+                                     const int32_t* mask, const float* table, int32_t n_tok, int32_t K,
+                                     int32_t S, vb200_transition tr, uint64_t seed, vb200_stream_t stream) {
+  if (n_tok == 0) return VB200_OK;
+  VB_REQUIRE(x_out && x0 && t_tok && table, "q_sample_philox: null pointer");
+  VB_REQUIRE(n_tok >= 0 && K >= 4 && S >= 1, "q_sample_philox: bad sizes n_tok=%d K=%d S=%d", n_tok, K, S);
+  int grid = (n_tok + 255) / 256;
+  const int cap = num_sms() * 8;
+  if (grid > cap) grid = cap;
+  VB_CHECK_CUDA(launch_pdl(q_sample_philox_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                           x_out, x0, t_tok, mask, table, n_tok, K, S, static_cast<int>(tr),
+                           static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

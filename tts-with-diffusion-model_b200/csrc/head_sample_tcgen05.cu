@@ -40,6 +40,7 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * 32 * ROW_BYTES + B
                            1024 /*align slack*/ + 256 /*barriers*/;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr int MODE_CE = 100;                    // epilogue = cross-entropy against target classes (no sampling)
 }  // namespace hs
 
 __device__ __forceinline__ void hs_bar_sync(int id, int n_threads) {
@@ -59,7 +60,8 @@ struct HsState {
 template <int NOISE>
 __global__ void __launch_bounds__(hs::THREADS, 1) head_sample_kernel(
     const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-    int32_t* __restrict__ x_out, const float* __restrict__ bias, const int32_t* __restrict__ x_t_all,
+    int32_t* __restrict__ x_out, float* __restrict__ loss_out, const float* __restrict__ bias,
+    const int32_t* __restrict__ x_t_all,
     const int32_t* __restrict__ row_utt, const int32_t* __restrict__ t_utt, const int32_t* __restrict__ utt,
     const float* __restrict__ table, int n_rows, int n_levels, int K, int Kd, int S, int transition,
     uint32_t seed_lo, uint32_t seed_hi) {
@@ -176,14 +178,16 @@ __global__ void __launch_bounds__(hs::THREADS, 1) head_sample_kernel(
       uint32_t key1 = 0, gid = 0;
       int b = 0;
       if (valid) {
-        b = row_utt[grow];
-        t = min(max(t_utt[b], 0), S - 1);
-        x_t = x_t_all[static_cast<size_t>(grow) * n_levels + level];
-        const int32_t* ur = utt + static_cast<size_t>(b) * VB200_U_STRIDE;
-        gid = static_cast<uint32_t>(ur[VB200_U_GID]);
-        key1 = static_cast<uint32_t>(grow - ur[VB200_U_RESP0]) * n_levels + level;
+        x_t = x_t_all[static_cast<size_t>(grow) * n_levels + level];     // MODE_CE: the target class
+        if (NOISE != MODE_CE) {
+          b = row_utt[grow];
+          t = min(max(t_utt[b], 0), S - 1);
+          const int32_t* ur = utt + static_cast<size_t>(b) * VB200_U_STRIDE;
+          gid = static_cast<uint32_t>(ur[VB200_U_GID]);
+          key1 = static_cast<uint32_t>(grow - ur[VB200_U_RESP0]) * n_levels + level;
+        }
       }
-      const bool need_arg = NOISE == VB200_NOISE_GREEDY || t == 0;
+      const bool need_arg = NOISE == VB200_NOISE_GREEDY || (NOISE != MODE_CE && t == 0);
       HsState st{-INFINITY, 0.f, 0.f, 0.f, 0.f, 0.f, -INFINITY, 0x7fffffff, 0};
       float win[32];                            // weights of the candidate chunk (local memory: written rarely)
 #pragma unroll
@@ -225,6 +229,14 @@ __global__ void __launch_bounds__(hs::THREADS, 1) head_sample_kernel(
               for (int i = 31; i >= 0; --i) if (v[i] == cmax) st.best_j = col0 + i;   // lowest index wins
             }
           }
+          if (NOISE == MODE_CE) {                       // the target's raw logit, through this thread's staging row
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(my_row + ((k ^ sw) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            const int dxt = x_t - col0;
+            if (dxt >= 0 && dxt < 32)
+              st.e_x = *reinterpret_cast<const float*>(my_row + (((dxt >> 2) ^ sw) << 4) + (dxt & 3) * 4);
+          }
           const float m_new = fmaxf(st.m, cmax);
           st.Z *= exp2f_fast((st.m - m_new) * kLog2e);            // 0 on the first chunk (m = -inf)
           st.m = m_new;
@@ -243,16 +255,18 @@ __global__ void __launch_bounds__(hs::THREADS, 1) head_sample_kernel(
           unpack2(acc, a0, a1);
           const float s_c = a0 + a1;
           st.Z += s_c;
-          // the chunk's weights go to this thread's staging row: class x_t is read back from it
+          if (NOISE != MODE_CE) {
+            // the chunk's weights go to this thread's staging row: class x_t is read back from it
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            *reinterpret_cast<float4*>(my_row + ((k ^ sw) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
-          const int dxt = x_t - col0;
-          if (dxt >= 0 && dxt < 32) {
-            st.e_x = *reinterpret_cast<const float*>(my_row + (((dxt >> 2) ^ sw) << 4) + (dxt & 3) * 4);
-            st.m_x = m_new;
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(my_row + ((k ^ sw) << 4)) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            const int dxt = x_t - col0;
+            if (dxt >= 0 && dxt < 32) {
+              st.e_x = *reinterpret_cast<const float*>(my_row + (((dxt >> 2) ^ sw) << 4) + (dxt & 3) * 4);
+              st.m_x = m_new;
+            }
+            if (col0 == (m_abs & ~31)) { st.e_m = v[0]; st.m_m = m_new; }   // K/2 is a multiple of 128
           }
-          if (col0 == (m_abs & ~31)) { st.e_m = v[0]; st.m_m = m_new; }   // K/2 is a multiple of 128
           // weighted reservoir: this chunk becomes the candidate with probability s_c / Z
           if (NOISE == VB200_NOISE_PHILOX) {
             if (u01(rw[c]) * st.Z < s_c) {
@@ -309,8 +323,11 @@ __global__ void __launch_bounds__(hs::THREADS, 1) head_sample_kernel(
           if (b1 > best || (b1 == best && j1 < best_j)) { best = b1; best_j = j1; }   // lowest index wins ties
         }
         const int cand_b = __float_as_int(my_x[8]);
-        int pick;
-        if (t == 0) {
+        int pick = 0;
+        if (NOISE == MODE_CE) {
+          // -log softmax(logits)[target] = max + ln Z - logit[target]; exactly one half saw the target
+          if (valid) loss_out[static_cast<size_t>(grow) * n_levels + level] = m_f + __logf(Z) - (st.e_x + my_x[2]);
+        } else if (t == 0) {
           pick = best_j;                                 // raw logits, no noise (ar_discrete.py:407,413)
         } else {
           // per-timestep scalars (see posterior_fast_kernel in d3pm.cu for the derivation)
@@ -344,7 +361,7 @@ __global__ void __launch_bounds__(hs::THREADS, 1) head_sample_kernel(
             else pick = (u01(fin.w) * Z < Zb) ? cand_b : cand;     // softmax(logits): merge the two candidates
           }
         }
-        if (valid) x_out[static_cast<size_t>(grow) * n_levels + level] = pick;
+        if (NOISE != MODE_CE && valid) x_out[static_cast<size_t>(grow) * n_levels + level] = pick;
       }
       hs_bar_sync(1 + quad, 64);                        // half 1 may overwrite its exchange words again
     }
@@ -360,7 +377,7 @@ __global__ void __launch_bounds__(hs::THREADS, 1) head_sample_kernel(
 }
 
 template <int NOISE>
-static int launch_head_sample(int32_t* x_out, const void* head_in, const void* W, const float* bias,
+static int launch_head_sample(int32_t* x_out, float* loss_out, const void* head_in, const void* W, const float* bias,
                               const int32_t* x_t, const int32_t* row_utt, const int32_t* t_utt,
                               const int32_t* utt, const float* table, int n_rows, int d, int n_levels,
                               int K, int S, int tr, uint64_t seed, cudaStream_t st) {
@@ -379,7 +396,7 @@ static int launch_head_sample(int32_t* x_out, const void* head_in, const void* W
     VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 2, ta, tb, x_out, bias, x_t, row_utt,
+  VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 2, ta, tb, x_out, loss_out, bias, x_t, row_utt,
                            t_utt, utt, table, n_rows, n_levels, K, d, S, tr, static_cast<uint32_t>(seed),
                            static_cast<uint32_t>(seed >> 32)));
   VB_CHECK_CUDA(cudaGetLastError());
@@ -396,10 +413,18 @@ int head_sample_fused(int32_t* x_out, const void* head_in, const void* W, const 
                       const float* table, int n_rows, int d, int n_levels, int K, int S, int tr, int noise,
                       uint64_t seed, cudaStream_t st) {
   if (noise == VB200_NOISE_GREEDY)
-    return launch_head_sample<VB200_NOISE_GREEDY>(x_out, head_in, W, bias, x_t, row_utt, t_utt, utt, table, n_rows,
+    return launch_head_sample<VB200_NOISE_GREEDY>(x_out, nullptr, head_in, W, bias, x_t, row_utt, t_utt, utt, table, n_rows,
                                                   d, n_levels, K, S, tr, seed, st);
-  return launch_head_sample<VB200_NOISE_PHILOX>(x_out, head_in, W, bias, x_t, row_utt, t_utt, utt, table, n_rows, d,
+  return launch_head_sample<VB200_NOISE_PHILOX>(x_out, nullptr, head_in, W, bias, x_t, row_utt, t_utt, utt, table, n_rows, d,
                                                 n_levels, K, S, tr, seed, st);
+}
+
+
+// classifier GEMM with per-token cross-entropy as its epilogue: loss[r, l] = -log softmax(logits[r, l, :])[target[r, l]]
+int head_ce_fused(float* loss_out, const void* head_in, const void* W, const float* bias, const int32_t* targets,
+                  int n_rows, int d, int n_levels, int K, cudaStream_t st) {
+  return launch_head_sample<hs::MODE_CE>(nullptr, loss_out, head_in, W, bias, targets, nullptr, nullptr, nullptr,
+                                         nullptr, n_rows, d, n_levels, K, 1, VB200_UNIFORM, 0, st);
 }
 
 }  // namespace vb200

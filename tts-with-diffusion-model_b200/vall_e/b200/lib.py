@@ -47,6 +47,8 @@ PROTOTYPES = {
     "vb200_head_posterior_sample": (
         [_p, _p, C.c_int, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, C.c_int, C.c_int, _p, _u64, _p],
         C.c_int),
+    "vb200_q_sample_philox": ([_p] * 5 + [_i32, _i32, _i32, C.c_int, _u64, _p], C.c_int),
+    "vb200_head_ce_loss": ([_p] * 5 + [_i32, _i32, _i32, _i32, _p], C.c_int),
     "vb200_workspace_bytes": ([_i64, _i64, _i32, _i32, C.c_int, C.POINTER(C.c_int64)], C.c_int64),
     "vb200_step_timesteps": ([_p, _i32, _i32, _p], C.c_int),
 }
@@ -171,6 +173,19 @@ def head_posterior_sample(x_out, logits, head_in, W, bias, x_t, row_utt, t_utt, 
         ptr(x_out), ptr(logits), dtype_code(logits.dtype), ptr(head_in), ptr(W), ptr(bias), n_rows, d,
         n_levels, K, ptr(x_t), ptr(row_utt), ptr(t_utt), ptr(utt), ptr(table), table.shape[0], transition,
         noise, ptr(uniforms), seed, stream()), "vb200_head_posterior_sample")
+
+
+def q_sample_philox(x_out, x0, t_tok, mask, table, K, transition, seed=0):
+    """x_t ~ q(x_t | x_0) with in-kernel Philox noise, O(1) per token."""
+    _check(load().vb200_q_sample_philox(ptr(x_out), ptr(x0), ptr(t_tok), ptr(mask), ptr(table), x0.numel(), K,
+                                        table.shape[0], transition, seed, stream()), "vb200_q_sample_philox")
+
+
+def head_ce_loss(loss, head_in, W, bias, targets, n_levels, K):
+    """loss[r, l] = -log softmax(head_in[r] W_l^T + b_l)[targets[r, l]] as the classifier GEMM's epilogue."""
+    n_rows, d = head_in.shape
+    _check(load().vb200_head_ce_loss(ptr(loss), ptr(head_in), ptr(W), ptr(bias), ptr(targets), n_rows, d,
+                                     n_levels, K, stream()), "vb200_head_ce_loss")
 
 
 def head_fused(d, K, noise) -> bool:

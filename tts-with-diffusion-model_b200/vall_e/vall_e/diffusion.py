@@ -195,6 +195,41 @@ class Diffusion(Base):
         out = x_t.to("cpu", non_blocking=False) if to_host else x_t
         return [r.long() for r in out.split(lay.t_resp, dim=0)]
 
+    # ------------------------------------------------------------------ training forward
+    @torch.no_grad()
+    def d3pm_loss(self, text_list: list[Tensor], proms_list: list[Tensor], resps_list: list[Tensor],
+                  t: Tensor | int | None = None, *, seed: int = 0, return_per_token: bool = False):
+        """The loss of the reference's training forward (ar_discrete.py:651-688) on the GPU, forward
+        only: x_t ~ q(x_t | x_0) with in-kernel noise (no K uniforms per token from the host),
+        logits = denoiser(x_t, t), cross-entropy against x_0 averaged over all response tokens.
+
+        ``t``: one timestep for the whole batch, a (B,) tensor of per-utterance timesteps, or None for
+        the reference's sweep t = 1 .. S-1 (loss averaged over the sweep).  The cross-entropy runs as
+        the classifier GEMM's epilogue, so no logits are materialised.  Returns a 0-dim float tensor
+        (and the (sum t'', 8) per-token losses of the last timestep when ``return_per_token``)."""
+        eng = self.engine()
+        dev = eng.w.device
+        ses = self._session(text_list, proms_list, [len(r) for r in resps_list], None)
+        lay, ws = ses.lay, ses.ws
+        x0 = torch.cat([r.reshape(len(r), self.n_levels) for r in resps_list]).to(device=dev, dtype=torch.int32)
+        table, tr = self._table(dev), _TRANSITIONS[self.transition]
+        if t is None:
+            sweep = [torch.full((lay.B,), ti, dtype=torch.int32, device=dev) for ti in range(1, self.timesteps)]
+        else:
+            tt = torch.as_tensor(t, dtype=torch.int32, device=dev)
+            sweep = [tt.expand(lay.B).contiguous() if tt.dim() == 0 else tt.contiguous()]
+        x_t = torch.empty_like(x0)
+        loss = torch.empty(lay.M_resp, self.n_levels, dtype=torch.float32, device=dev)
+        total = torch.zeros((), dtype=torch.float32, device=dev)
+        for i, t_utt in enumerate(sweep):
+            t_tok = t_utt[lay.resp_row_utt.long()].repeat_interleave(self.n_levels).contiguous()
+            L.q_sample_philox(x_t.view(-1), x0.view(-1), t_tok, None, table, self.num_classes, tr, seed=seed + i)
+            head_in = eng.forward(lay, ws, x_t, t_utt, use_time=True, head=False)
+            L.head_ce_loss(loss, head_in, eng.w.w_cls, eng.w.b_cls, x0, self.n_levels, self.num_classes)
+            total += loss.mean()
+        total /= len(sweep)
+        return (total, loss, x_t) if return_per_token else total
+
     def _session(self, text_list, proms_list, resp_lens, gids):
         """Sessions (buffers + captured step graph) are cached per shape signature, so a stream of
         same-shape batches pays layout upload and graph capture once."""
