@@ -49,6 +49,24 @@ elif what == "gemm_out":     # to_out at the bench shape: K = 1024, fp32 residua
     x = torch.randn(M, 1024, device=dev)
     for _ in range(3):
         L.gemm_bf16(x, A, W, bias, x, L.EPI_BIAS_RESIDUAL)
+elif what == "head_sample":  # fused classifier + reverse step at the bench shape
+    sys.path.insert(0, str(ROOT / "tts-with-diffusion-model_b200"))
+    from vall_e.vall_e import d3pm
+    S, K, d, B = 51, 1024, 1024, 256
+    rows = 750 * B
+    tab = d3pm.scalar_table(S, K, "absorbing").to(dev)
+    W = (torch.randn(8 * K, d, device=dev) * 0.03).bfloat16()
+    bias = torch.randn(8 * K, device=dev)
+    head_in = torch.randn(rows, d, device=dev).bfloat16()
+    x_t = torch.full((rows, 8), K // 2, dtype=torch.int32, device=dev)
+    row_utt = torch.arange(B, dtype=torch.int32, device=dev).repeat_interleave(750)
+    utt = torch.zeros(B, L.U_STRIDE, dtype=torch.int32, device=dev)
+    utt[:, L.U_RESP0] = torch.arange(B, device=dev, dtype=torch.int32) * 750
+    t_utt = torch.full((B,), 30, dtype=torch.int32, device=dev)
+    o = torch.empty(rows, 8, dtype=torch.int32, device=dev)
+    for _ in range(3):
+        L.head_posterior_sample(o, None, head_in, W, bias, x_t, row_utt, t_utt, utt, tab, 8, K, L.ABSORBING,
+                                L.NOISE_PHILOX, seed=1)
 elif what == "posterior":
     sys.path.insert(0, str(ROOT / "tts-with-diffusion-model_b200"))
     from vall_e.vall_e import d3pm

@@ -167,10 +167,12 @@ def posterior_sample_from_logits(x_out, post_out, logits, ld_logits, x_t, row_ut
 
 def head_posterior_sample(x_out, logits, head_in, W, bias, x_t, row_utt, t_utt, utt, table, n_levels, K,
                           transition, noise, uniforms=None, seed=0):
-    """classifier GEMM into the caller's `logits` scratch + reverse step on them (one C call)."""
+    """classifier + reverse step in one C call: one kernel (reverse step as the GEMM epilogue) when
+    head_fused(), else GEMM into the caller's `logits` scratch (required then) + standalone kernel."""
     n_rows, d = head_in.shape
     _check(load().vb200_head_posterior_sample(
-        ptr(x_out), ptr(logits), dtype_code(logits.dtype), ptr(head_in), ptr(W), ptr(bias), n_rows, d,
+        ptr(x_out), ptr(logits), dtype_code(logits.dtype) if logits is not None else dtype_code(torch.float16),
+        ptr(head_in), ptr(W), ptr(bias), n_rows, d,
         n_levels, K, ptr(x_t), ptr(row_utt), ptr(t_utt), ptr(utt), ptr(table), table.shape[0], transition,
         noise, ptr(uniforms), seed, stream()), "vb200_head_posterior_sample")
 
