@@ -41,6 +41,13 @@ elif what == "gemm_big":     # FFN1 at the bench shape (256 utterances x 1027 ro
     out = torch.empty(M, 4096, dtype=torch.bfloat16, device=dev)
     for _ in range(3):
         L.gemm_bf16(out, A, W, bias, None, L.EPI_BIAS_GELU)
+elif what == "gemm_qkv":     # to_qkv at the bench shape: plain bf16 output
+    M = 262912
+    A = torch.randn(M, 1024, device=dev).bfloat16()
+    W = torch.randn(3072, 1024, device=dev).bfloat16()
+    out = torch.empty(M, 3072, dtype=torch.bfloat16, device=dev)
+    for _ in range(3):
+        L.gemm_bf16(out, A, W, None, None, L.EPI_NONE)
 elif what == "gemm_out":     # to_out at the bench shape: K = 1024, fp32 residual reduce-add epilogue
     M = 262912
     A = torch.randn(M, 1024, device=dev).bfloat16()
