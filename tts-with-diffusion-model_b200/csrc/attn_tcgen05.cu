@@ -358,6 +358,16 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
       mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); mbar_init(&buf_free[i], 4);
     }
     fence_barrier_init();
+    // Q and the first K / V block go out before the block-wide sync below (TMEM allocation, barrier
+    // visibility for the other warps): the first TMA round trip is on every CTA's critical path.
+    pdl_launch_dependents();
+    pdl_wait();                                   // qkv is the previous kernel's output
+    mbar_arrive_expect_tx(q_full, TILE_BYTES);
+    tma_load_2d(s_q, &tm_qkv, q_full, h * HD, row0 + qt * BQ);
+    mbar_arrive_expect_tx(&k_full[0], TILE_BYTES);
+    tma_load_2d(s_k, &tm_qkv, &k_full[0], d + h * HD, row0);
+    mbar_arrive_expect_tx(&v_full[0], TILE_BYTES);
+    tma_load_2d(s_v, &tm_qkv, &v_full[0], 2 * d + h * HD, row0);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -379,11 +389,7 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     const bool leader = elect_one();
-    if (leader) {
-      mbar_arrive_expect_tx(q_full, TILE_BYTES);
-      tma_load_2d(s_q, &tm_qkv, q_full, h * HD, row0 + qt * BQ);
-    }
-    for (int j = 0; j < nblk; ++j) {
+    for (int j = 1; j < nblk; ++j) {              // Q and block 0 were issued in the prologue
       const int s = j % KV_STAGES;
       const uint32_t ph = (j / KV_STAGES) & 1;
       mbar_wait(&k_empty[s], ph ^ 1);
