@@ -255,47 +255,10 @@ __global__ void __launch_bounds__(256) adaln_rows_kernel(
     }
     const int lvl = level_utt[row_utt[r]];
     if (lvl != cached) {                               // warp-uniform
-      const float* gp = table + static_cast<size_t>(lvl) * 2 * d;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp + i * 256 + lane * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + i * 256 + lane * 8 + 4));
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(gp + d + i * 256 + lane * 8));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(gp + d + i * 256 + lane * 8 + 4));
-        g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w;
-        g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
-        bt[i][0] = b0.x; bt[i][1] = b0.y; bt[i][2] = b0.z; bt[i][3] = b0.w;
-        bt[i][4] = b1.x; bt[i][5] = b1.y; bt[i][6] = b1.z; bt[i][7] = b1.w;
-      }
+      adaln_load_params<NV>(table, lvl, lane, g, bt);
       cached = lvl;
     }
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s += v[i][e];
-    const float mean = warp_sum(s) * (1.0f / d);
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) { const float dv = v[i][e] - mean; q += dv * dv; }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / d) + eps);
-    __nv_bfloat16* orow = out + static_cast<size_t>(r) * d;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float y[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float h = (v[i][e] - mean) * rstd;
-        h = c * (1.f - k * h) * h;
-        y[e] = fmaf(g[i][e], h, bt[i][e]);
-      }
-      uint4 o;
-      o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-      o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
-      *reinterpret_cast<uint4*>(orow + i * 256 + lane * 8) = o;
-    }
+    adaln_row_finish<NV>(v, g, bt, out + static_cast<size_t>(r) * d, lane, eps, k, c);
   }
 }
 
