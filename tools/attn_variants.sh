@@ -10,6 +10,6 @@ for spec in "$@"; do
   name="${spec%%:*}"; defs="${spec#*:}"
   nvcc $FLAGS $defs -c csrc/attn_tcgen05.cu -o build/variants/attn_$name.o
   nvcc -shared -o build/variants/lib$name.so build/obj/api.o build/obj/elementwise.o build/obj/d3pm.o \
-       build/obj/gemm_tcgen05.o build/obj/debug_simt.o build/variants/attn_$name.o -gencode arch=compute_100a,code=sm_100a
+       build/obj/gemm_tcgen05.o build/obj/head_sample_tcgen05.o build/obj/debug_simt.o build/variants/attn_$name.o -gencode arch=compute_100a,code=sm_100a
   echo "built build/variants/lib$name.so ($defs)"
 done
