@@ -405,3 +405,40 @@ def test_head_posterior_sample_fused_vs_separate_kernels(L):
             chi2 += (rest_obs - rest_exp) ** 2 / rest_exp
         dof = max(int(keep.sum().item()), 2)
         assert chi2 < dof + 6 * math.sqrt(2 * dof), (xt_val, chi2, dof)
+
+
+@pytest.mark.parametrize("rows,K,levels,d", [(77, 1024, 8, 128), (600, 512, 3, 64), (1000, 256, 1, 256)])
+def test_head_ce_loss_matches_torch(L, rows, K, levels, d):
+    """vb200_head_ce_loss (cross-entropy as the classifier GEMM's epilogue, no logits in memory)
+    against torch's cross-entropy on fp32 logits of the same bf16 operands."""
+    g = torch.Generator().manual_seed(rows)
+    head_in = torch.randn(rows, d, generator=g).bfloat16().to(DEV)
+    W = (torch.randn(levels * K, d, generator=g) * 0.4).bfloat16().to(DEV)
+    bias = torch.randn(levels * K, generator=g).to(DEV)
+    tgt = torch.randint(0, K, (rows, levels), generator=g, dtype=torch.int32).to(DEV)
+    tgt[0, 0], tgt[-1, -1] = 0, K - 1                    # first / last class of a level
+    loss = torch.full((rows, levels), float("nan"), device=DEV)
+    L.head_ce_loss(loss, head_in, W, bias, tgt, levels, K)
+    logits = (head_in.float() @ W.float().t() + bias).view(rows, levels, K)
+    ref = torch.nn.functional.cross_entropy(logits.reshape(-1, K), tgt.reshape(-1).long(), reduction="none")
+    assert (loss.view(-1) - ref).abs().max().item() < 2e-3
+
+
+def test_q_sample_philox_uniform_transition_law(L):
+    """O(1) Philox q_sample, uniform transition: P(keep) and the spread over the other classes."""
+    from vall_e.vall_e import d3pm as pd
+    K, S, n, t0, x0 = 64, 20, 400000, 9, 17
+    table = pd.scalar_table(S, K, "uniform").to(DEV)
+    out = torch.empty(n, dtype=torch.int32, device=DEV)
+    L.q_sample_philox(out, torch.full((n,), x0, dtype=torch.int32, device=DEV),
+                      torch.full((n,), t0, dtype=torch.int32, device=DEV), None, table, K, L.UNIFORM, seed=4)
+    row = table[t0].cpu().double()
+    w_keep, w_off = math.exp(row[L.TAB_LOG_KEEP].item()), math.exp(row[L.TAB_LOG_OFF].item())
+    p_keep = w_keep / (w_keep + (K - 1) * w_off)
+    counts = torch.bincount(out.cpu().long(), minlength=K).double()
+    assert abs(counts[x0].item() - p_keep * n) < 6 * math.sqrt(n * p_keep * (1 - p_keep)) + 1
+    others = torch.cat([counts[:x0], counts[x0 + 1:]])
+    exp_o = (n - p_keep * n) / (K - 1)
+    chi2 = (((others - exp_o) ** 2) / exp_o).sum().item()
+    assert chi2 < (K - 2) + 6 * math.sqrt(2 * (K - 2)), chi2
+    assert int(out.min()) >= 0 and int(out.max()) < K
