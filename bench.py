@@ -1,6 +1,7 @@
 """Benchmark of the D3PM denoising-sampler hot path (BASELINE.json metric: codec tokens/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c4|c5]
+                    [--denoise-steps S] [--transition absorbing|uniform]
 
 Workload (default c3 = BASELINE.json configs[2], the configuration the throughput metric is
 quoted on; it fits one GPU): full denoiser (d=1024, 12 layers, 16 heads, K=1024, 8 levels), 256
@@ -404,7 +405,16 @@ def main():
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--denoise-steps", type=int, default=None,
+                    help="override the workload's number of denoise steps (BASELINE configs[4] sweeps 10/25/50/100)")
+    ap.add_argument("--transition", default=None, choices=["absorbing", "uniform"],
+                    help="override the workload's transition (BASELINE configs[4] sweeps both)")
     args = ap.parse_args()
+    if args.denoise_steps is not None or args.transition is not None:
+        B, t_txt, t_prom, t_resp, timesteps, transition = WORKLOADS[args.workload]
+        WORKLOADS[args.workload] = (B, t_txt, t_prom, t_resp,
+                                    timesteps if args.denoise_steps is None else args.denoise_steps + 1,
+                                    transition if args.transition is None else args.transition)
     if args.impl == "reference":
         run_reference(args, args.workload)
     else:
