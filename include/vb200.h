@@ -212,6 +212,14 @@ int vb200_head_ce_loss(float* loss, const void* head_in_bf16, const void* W_bf16
 int64_t vb200_workspace_bytes(int64_t M, int64_t M_resp, int32_t d, int32_t n_out,
                               vb200_dtype logits_dtype, int64_t* sizes);
 
+/* Hand-off to the EnCodec decoder (reference emb/qnt.py:32-49 `decode(codes (b q t))`,
+ * fed one utterance at a time through `rearrange(resps, "t q -> 1 q t")` in decode_to_file): the packed
+ * int32 codes (sum_b T_resp_b, n_levels) of a whole batch -> ONE int64 tensor (B, n_levels, T_max) in the
+ * decoder's layout, frames beyond an utterance's length filled with `pad`.  utt records give each
+ * utterance's first response row (VB200_U_RESP0) and length (VB200_U_TRESP). */
+int vb200_codes_to_bqt(int64_t* out, const int32_t* codes, const int32_t* utt, int32_t B,
+                       int32_t n_levels, int32_t T_max, int64_t pad, vb200_stream_t stream);
+
 /* reverse-loop helper (ar_discrete.py:750): t_utt[b] -= 1 for all b, on device (graph-capturable) */
 int vb200_step_timesteps(int32_t* t_utt, int32_t B, int32_t delta, vb200_stream_t stream);
 

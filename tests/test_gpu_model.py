@@ -361,3 +361,40 @@ def test_training_forward_loss_vs_oracle_and_torch():
     rest_exp = n - (p[5] + p[K // 2]).item() * n
     rest_obs = n - counts[5].item() - counts[K // 2].item()
     assert abs(rest_obs - rest_exp) < 6 * math.sqrt(max(rest_exp, 1.0)) + 1
+
+
+def test_encodec_handoff_bqt_layout_matches_reference_rearrange():
+    """the batch hand-off to the EnCodec decoder (emb/qnt.py:32-49).  The (B, 8, T_max)
+    tensor must hold, per utterance, exactly what the reference builds one utterance at a time with
+    rearrange(resps, "t q -> 1 q t") (emb/qnt.py:46), zero-padded past its length.  Bit-exact."""
+    from vall_e.b200 import lib as L
+    K, d, h, nl, S = 64, 128, 2, 2, 8
+    m, _ = _make(K, d, h, nl, S, "absorbing", seed=4)
+    lens = [(4, 10, 40), (6, 7, 301), (3, 5, 1)]
+    text, proms, _ = _batch(K, lens, 9)
+    text, proms = [x.to(DEV) for x in text], [x.to(DEV) for x in proms]
+    rl = [x[2] for x in lens]
+    codes = m.generate_audio(text, proms, resp_lens=rl, seed=3)
+    bqt, frames = m.generate_audio(text, proms, resp_lens=rl, seed=3, as_bqt=True)
+    assert frames == rl and bqt.shape == (3, 8, 301) and bqt.dtype == torch.int64
+    for b, c in enumerate(codes):
+        ref = c.t()[None]                                   # "t q -> 1 q t"
+        assert torch.equal(bqt[b:b + 1, :, :rl[b]], ref)
+        assert int(bqt[b, :, rl[b]:].abs().sum()) == 0
+    host, _ = m.generate_audio(text, proms, resp_lens=rl, seed=3, as_bqt=True, to_host=True)
+    assert not host.is_cuda and torch.equal(host, bqt.cpu())
+    # the kernel on its own, other level counts and a non-zero pad value; empty batch is a no-op
+    g = torch.Generator().manual_seed(0)
+    for n_levels, tl in ((1, [5, 300, 17]), (3, [257, 256, 255, 1])):
+        packed = torch.randint(0, 1024, (sum(tl), n_levels), generator=g, dtype=torch.int32)
+        utt = torch.zeros(len(tl), L.U_STRIDE, dtype=torch.int32)
+        utt[:, L.U_TRESP] = torch.tensor(tl, dtype=torch.int32)
+        utt[:, L.U_RESP0] = torch.tensor([0] + list(np.cumsum(tl)[:-1]), dtype=torch.int32)
+        out = torch.empty(len(tl), n_levels, max(tl), dtype=torch.int64, device=DEV)
+        L.codes_to_bqt(out, packed.to(DEV), utt.to(DEV), pad=-7)
+        ref = torch.full(out.shape, -7, dtype=torch.int64)
+        for b, chunk in enumerate(packed.split(tl)):
+            ref[b, :, :tl[b]] = chunk.t().long()
+        assert torch.equal(out.cpu(), ref)
+    L.codes_to_bqt(torch.empty(0, 8, 4, dtype=torch.int64, device=DEV), torch.empty(0, 8, dtype=torch.int32, device=DEV),
+                   torch.empty(0, L.U_STRIDE, dtype=torch.int32, device=DEV))

@@ -283,6 +283,23 @@ __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(
   }
 }
 
+// codes (sum T_resp, L) int32 -> (B, L, T_max) int64, one thread per (utterance, frame): the L codes of
+// a frame are one contiguous read, every level's row of the output is written coalesced along t.
+__global__ void __launch_bounds__(256) codes_to_bqt_kernel(
+    int64_t* __restrict__ out, const int32_t* __restrict__ codes, const int32_t* __restrict__ utt,
+    int n_levels, int T_max, int64_t pad) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T_max) return;
+  const int32_t* u = utt + b * VB200_U_STRIDE;
+  const bool valid = t < u[VB200_U_TRESP];
+  const int32_t* src = codes + (static_cast<size_t>(u[VB200_U_RESP0]) + t) * n_levels;
+  int64_t* dst = out + static_cast<size_t>(b) * n_levels * T_max + t;
+  for (int l = 0; l < n_levels; ++l) dst[static_cast<size_t>(l) * T_max] = valid ? static_cast<int64_t>(src[l]) : pad;
+}
+
 static int row_grid(int rows, int wpb) {
   int grid = (rows + wpb - 1) / wpb;
   const int cap = num_sms() * 16;
@@ -384,6 +401,18 @@ extern "C" int vb200_gather_rows_bf16(void* out_bf16, const float* x, const int3
   if (n_rows <= 0) return VB200_OK;
   VB_CHECK_CUDA(launch_pdl(gather_rows_bf16_kernel, dim3(row_grid(n_rows, 8)), dim3(256), 0,
                            static_cast<cudaStream_t>(stream), 1, static_cast<__nv_bfloat16*>(out_bf16), x, row_index, n_rows, d));
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
+}
+
+extern "C" int vb200_codes_to_bqt(int64_t* out, const int32_t* codes, const int32_t* utt, int32_t B,
+                                  int32_t n_levels, int32_t T_max, int64_t pad, vb200_stream_t stream) {
+  VB_REQUIRE(B >= 0 && T_max >= 0 && n_levels > 0, "codes_to_bqt: bad sizes B=%d n_levels=%d T_max=%d", B, n_levels, T_max);
+  if (B == 0 || T_max == 0) return VB200_OK;
+  VB_REQUIRE(out && codes && utt, "codes_to_bqt: null pointer");
+  VB_REQUIRE(B <= 65535, "codes_to_bqt: B=%d exceeds the grid's y extent", B);
+  VB_CHECK_CUDA(launch_pdl(codes_to_bqt_kernel, dim3((T_max + 255) / 256, B), dim3(256), 0,
+                           static_cast<cudaStream_t>(stream), 1, out, codes, utt, n_levels, T_max, pad));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

@@ -26,6 +26,17 @@ def _load(path, device):
     return torch.load(path, weights_only=False).to(device)
 
 
+def decode_batch_to_files(qnt, codes_bqt, frames, paths, hop: int = 320):
+    """EnCodec hand-off for a batch: ONE ``qnt.decode`` call (reference emb/qnt.py:32-41,
+    which already takes ``(b q t)``) on the ``(B, 8, T_max)`` tensor ``Diffusion.generate_audio(...,
+    as_bqt=True)`` returns, instead of the reference's one-utterance-at-a-time ``decode_to_file``
+    (:44-48); each waveform is cut at its own length (``hop`` samples per frame: 24 kHz / 75 frames/s)."""
+    import soundfile
+    wavs, sr = qnt.decode(codes_bqt)
+    for wav, n, path in zip(wavs.cpu(), frames, paths):
+        soundfile.write(str(path), wav[0, : n * hop], sr)
+
+
 def main():
     parser = argparse.ArgumentParser("VALL-E TTS")
     parser.add_argument("text")

@@ -51,6 +51,7 @@ PROTOTYPES = {
     "vb200_head_ce_loss": ([_p] * 5 + [_i32, _i32, _i32, _i32, _p], C.c_int),
     "vb200_workspace_bytes": ([_i64, _i64, _i32, _i32, C.c_int, C.POINTER(C.c_int64)], C.c_int64),
     "vb200_step_timesteps": ([_p, _i32, _i32, _p], C.c_int),
+    "vb200_codes_to_bqt": ([_p, _p, _p, _i32, _i32, _i32, _i64, _p], C.c_int),
 }
 
 _lib = None
@@ -131,6 +132,14 @@ def gather_rows_bf16(out, x, row_index):
     n, d = out.shape
     _check(load().vb200_gather_rows_bf16(ptr(out), ptr(x), ptr(row_index), n, d, stream()),
            "vb200_gather_rows_bf16")
+
+
+def codes_to_bqt(out, codes, utt, pad=0):
+    """packed int32 codes (sum t'', l) -> int64 (B, l, T_max) for the EnCodec decoder (emb/qnt.py:32-49)."""
+    B, n_levels, T_max = out.shape
+    assert out.dtype == torch.int64 and codes.dtype == torch.int32 and out.is_contiguous() and codes.is_contiguous()
+    _check(load().vb200_codes_to_bqt(ptr(out), ptr(codes), ptr(utt), B, n_levels, T_max, int(pad), stream()),
+           "vb200_codes_to_bqt")
 
 
 def gemm_bf16(out, A, W, bias=None, residual=None, epi=EPI_NONE, simt=False):

@@ -162,7 +162,7 @@ class Diffusion(Base):
     def generate_audio(self, text_list: list[Tensor], proms_list: list[Tensor], resps_list=None, *,
                        resp_lens: list[int] | None = None, seed: int = 0, greedy: bool = False,
                        uniforms_fn=None, gids=None, use_graph: bool = True, trace: list | None = None,
-                       to_host: bool = False):
+                       to_host: bool = False, as_bqt: bool = False):
         """x_T -> x_0 for a batch of utterances; returns [LongTensor (t'', 8)].
 
         x_T is all ``mask_id`` for the absorbing transition (ar_discrete.py:699) and uniform random
@@ -171,6 +171,9 @@ class Diffusion(Base):
         ``resps_list`` (optional) supplies x_T explicitly.  ``uniforms_fn(t)`` switches to the
         reference's noise convention (supplied U[0,1) of shape (sum t'' * 8, K)) for parity runs.
         ``to_host`` returns CPU tensors (one device->host copy of the int32 codes).
+        ``as_bqt`` returns ``(LongTensor (B, 8, T_max), [t''])`` instead: the whole batch in the layout
+        ``emb/qnt.py:32-49 decode(codes (b q t))`` takes, zero-padded, so the EnCodec stage decodes
+        the batch in one call instead of one ``t q -> 1 q t`` utterance at a time.
         """
         eng = self.engine()
         dev = eng.w.device
@@ -192,6 +195,10 @@ class Diffusion(Base):
         noise = L.NOISE_GREEDY if greedy else (L.NOISE_UNIFORMS if uniforms_fn is not None else L.NOISE_PHILOX)
         ses.run(self._table(dev), self.timesteps, _TRANSITIONS[self.transition], noise=noise, seed=seed,
                 uniforms_fn=uniforms_fn, use_graph=use_graph, n_levels=self.n_levels, trace=trace)
+        if as_bqt:        # one (B, 8, T_max) int64 tensor in the EnCodec decoder's layout + the frame counts
+            bqt = torch.empty(lay.B, self.n_levels, max(lay.t_resp), dtype=torch.int64, device=dev)
+            L.codes_to_bqt(bqt, x_t, lay.utt, pad=0)
+            return (bqt.cpu() if to_host else bqt), list(lay.t_resp)
         out = x_t.to("cpu", non_blocking=False) if to_host else x_t
         return [r.long() for r in out.split(lay.t_resp, dim=0)]
 
