@@ -17,6 +17,10 @@
 
 #include "common.cuh"
 
+#ifndef VB200_GEMM_EARLY_LOAD
+#define VB200_GEMM_EARLY_LOAD 1
+#endif
+
 namespace vb200 {
 
 namespace gemm {
@@ -33,7 +37,7 @@ template <int CTAS, int BN> struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = STAGE_BYTES == 48 * 1024 ? 4 : 6;
+  static constexpr int STAGES = (4 * 48 * 1024) / STAGE_BYTES;   // 4 x 48 KB, 6 x 32 KB, 8 x 24 KB
 };
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;   // 320
@@ -107,6 +111,23 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], EPI_WARPS * CTAS); }
     fence_barrier_init();
+#if VB200_GEMM_EARLY_LOAD
+    // single-CTA kernels: the first ring's worth of loads of this CTA's first tile goes out before
+    // the block-wide sync below (TMEM allocation): the first TMA round trip is on the critical path
+    // of the one-wave launches of a single utterance
+    if (CTAS == 1 && tile0 < num_tiles) {
+      pdl_launch_dependents();
+      pdl_wait();                                   // A is an earlier kernel's output
+      const int m_row = (tile0 / num_n) * BM, n_row = (tile0 % num_n) * BN;
+      const int n_pre = num_kb < STAGES ? num_kb : STAGES;
+      for (int kb = 0; kb < n_pre; ++kb) {
+        uint8_t* sa = smem + kb * STAGE_BYTES;
+        mbar_arrive_expect_tx(&full[kb], STAGE_BYTES);
+        tma_load_2d(sa, &tm_a, &full[kb], kb * BK, m_row);
+        tma_load_2d(sa + A_BYTES, &tm_b, &full[kb], kb * BK, n_row);
+      }
+    }
+#endif
   }
   if (warp == 1) {
     if (CTAS == 2) { tmem_alloc_pair(tmem_slot, TMEM_COLS); tmem_relinquish_pair(); }
@@ -129,10 +150,17 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
       // ------------------------------------------------------------ TMA producer
       const bool leader = elect_one();
       int stage = 0; uint32_t phase = 0;
+      int kb0 = 0;
+#if VB200_GEMM_EARLY_LOAD
+      if (CTAS == 1) {                              // the prologue already requested these k-blocks
+        kb0 = num_kb < STAGES ? num_kb : STAGES;
+        if (kb0 == STAGES) phase = 1; else stage = kb0;
+      }
+#endif
       for (int tile = tile0; tile < num_tiles; tile += tile_stride) {
         const int m_blk = tile / num_n, n_blk = tile % num_n;
         const int m_row = (m_blk * CTAS + cta_rank) * BM, n_row = n_blk * BN + cta_rank * B_ROWS;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           if (leader) {
@@ -150,6 +178,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        kb0 = 0;
       }
     }
   } else if (warp == 1) {
@@ -309,12 +338,23 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
   const long t_pair = static_cast<long>((((M + 2 * BM - 1) / (2 * BM)) * nn + sms / 2 - 1) / (sms / 2)) * 135;
   const long t_narrow = N > 128 ? static_cast<long>((mt * ((N + 127) / 128) + sms - 1) / sms) * 99 : (1l << 40);
   int ctas = forced;
-  bool narrow = false;
+  bool narrow = false, narrow64 = false;
   if (ctas != 1 && ctas != 2) {
     ctas = t_pair <= t_wide ? 2 : 1;
     if (t_narrow < (ctas == 2 ? t_pair : t_wide)) { ctas = 1; narrow = true; }
+    // 128x64 tiles (fp32 outputs only: the two residual GEMMs): when even the 128-wide tiling leaves
+    // SMs idle (one utterance: 72 tiles), twice the CTAs each pull 3/4 of the operand bytes
+    static int n64 = -1;
+    if (n64 < 0) {
+      const char* e = getenv("VB200_GEMM_N64");
+      n64 = e ? atoi(e) : 1;
+    }
+    if (sizeof(OutT) == 4 && n64 && narrow && N > 64) {
+      const long t_n64 = static_cast<long>((mt * ((N + 63) / 64) + sms - 1) / sms) * 75;
+      if (t_n64 < t_narrow) narrow64 = true;
+    }
   }
-  const int bn = narrow ? 128 : BN;
+  const int bn = narrow64 ? 64 : (narrow ? 128 : BN);
   CUtensorMap ta, tb, tout;
   int rc = cached_tmap(&ta, VB200_BF16, A, K, M, static_cast<uint64_t>(K) * 2, BK, BM);
   if (rc != VB200_OK) return rc;
@@ -326,7 +366,17 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
   const int tiles = ((M + BM * ctas - 1) / (BM * ctas)) * ((N + bn - 1) / bn);
   const int groups = num_sms() / ctas;
   const int grid = (tiles < groups ? tiles : groups) * ctas;
-  if (narrow) {
+  if (narrow64) {
+    if constexpr (sizeof(OutT) == 4) {
+      auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 64>;
+      static bool configured = false;
+      if (!configured) {
+        VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        configured = true;
+      }
+      VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K));
+    }
+  } else if (narrow) {
     auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 128>;
     static bool configured = false;
     if (!configured) {
