@@ -323,36 +323,38 @@ template <int EPI, typename OutT>
 static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, const float* bias, int M, int N,
                        int K, cudaStream_t st) {
   using namespace gemm;
-  // Three tilings, picked by estimated waves x cycles per k-step (tools/mma_bench.cu):
-  //   CTA pair 256x256 (~135 cycles, half as many schedulable units), one CTA 128x256 (~163),
-  //   one CTA 128x128 (~99, twice the tiles: for one utterance at a time, M ~ 1000).
-  // VB200_GEMM_CTAS=1|2 forces the CTA count (A/B measurements).
-  static int forced = -1;
-  if (forced < 0) {
-    const char* e = getenv("VB200_GEMM_CTAS");
-    forced = e ? atoi(e) : 0;
-  }
+  // Four tilings, picked by estimated cycles = waves x k-steps x cycles per MMA (tools/mma_bench.cu):
+  //   CTA pair 256x256 (~135 cycles per k-step, half as many schedulable units, + ~5 000 cycles per
+  //   launch: cluster scheduling, pair TMEM allocation, two cluster-wide syncs — measured with
+  //   tools/gemm_small_probe.py, it only matters for one or two utterances at a time),
+  //   one CTA 128x256 (~163), one CTA 128x128 (~99, twice the tiles),
+  //   one CTA 128x64 (~75; fp32 outputs only: the two residual GEMMs) when even the 128-wide tiling
+  //   leaves SMs idle (one utterance: 72 tiles) — twice the CTAs each pull 3/4 of the operand bytes,
+  //   and a single-wave launch is bound by how fast an SM ingests operands from L2 (~60 B/clk).
   constexpr int BN = 256;
   const int sms = num_sms(), mt = (M + BM - 1) / BM, nn = (N + BN - 1) / BN;
-  const long t_wide = static_cast<long>((mt * nn + sms - 1) / sms) * 163;
-  const long t_pair = static_cast<long>((((M + 2 * BM - 1) / (2 * BM)) * nn + sms / 2 - 1) / (sms / 2)) * 135;
-  const long t_narrow = N > 128 ? static_cast<long>((mt * ((N + 127) / 128) + sms - 1) / sms) * 99 : (1l << 40);
-  int ctas = forced;
+  const long ksteps = static_cast<long>((K + BK - 1) / BK) * (BK / 16);
+  auto waves = [](long tiles, long units) { return (tiles + units - 1) / units; };
+  const long t_wide = waves(static_cast<long>(mt) * nn, sms) * ksteps * 163;
+  const long t_pair = waves(static_cast<long>((M + 2 * BM - 1) / (2 * BM)) * nn, sms / 2) * ksteps * 135 + 5000;
+  const long t_narrow = N > 128 ? waves(static_cast<long>(mt) * ((N + 127) / 128), sms) * ksteps * 99 : (1l << 60);
+  const long t_n64 = (sizeof(OutT) == 4 && N > 64) ? waves(static_cast<long>(mt) * ((N + 63) / 64), sms) * ksteps * 75
+                                                   : (1l << 60);
+  int ctas = t_pair <= t_wide ? 2 : 1;
   bool narrow = false, narrow64 = false;
-  if (ctas != 1 && ctas != 2) {
-    ctas = t_pair <= t_wide ? 2 : 1;
-    if (t_narrow < (ctas == 2 ? t_pair : t_wide)) { ctas = 1; narrow = true; }
-    // 128x64 tiles (fp32 outputs only: the two residual GEMMs): when even the 128-wide tiling leaves
-    // SMs idle (one utterance: 72 tiles), twice the CTAs each pull 3/4 of the operand bytes
-    static int n64 = -1;
-    if (n64 < 0) {
-      const char* e = getenv("VB200_GEMM_N64");
-      n64 = e ? atoi(e) : 1;
-    }
-    if (sizeof(OutT) == 4 && n64 && narrow && N > 64) {
-      const long t_n64 = static_cast<long>((mt * ((N + 63) / 64) + sms - 1) / sms) * 75;
-      if (t_n64 < t_narrow) narrow64 = true;
-    }
+  long best = ctas == 2 ? t_pair : t_wide;
+  if (t_narrow < best) { ctas = 1; narrow = true; best = t_narrow; }
+  if (t_n64 < best) { ctas = 1; narrow = false; narrow64 = true; best = t_n64; }
+  // VB200_GEMM_TILE=pair|wide|narrow|n64 forces a tiling (A/B measurements, tools/gemm_small_probe.py)
+  static int tile_forced = -1;
+  if (tile_forced < 0) {
+    const char* e = getenv("VB200_GEMM_TILE");
+    tile_forced = !e ? 0 : e[0] == 'p' ? 1 : e[0] == 'w' ? 2 : (e[0] == 'n' && e[1] == 'a') ? 3 : (e[0] == 'n' && e[1] == '6') ? 4 : 0;
+  }
+  if (tile_forced) {
+    ctas = tile_forced == 1 ? 2 : 1;
+    narrow = tile_forced == 3 && N > 128;
+    narrow64 = tile_forced == 4 && sizeof(OutT) == 4 && N > 64;
   }
   const int bn = narrow64 ? 64 : (narrow ? 128 : BN);
   CUtensorMap ta, tb, tout;
