@@ -46,12 +46,6 @@ typedef enum {
   VB200_EPI_BIAS_RESIDUAL = 3  /* out = residual + acc + bias  (fp32)     (to_out / ffn.block.3 + PrenormResidual, base.py:129,193-194) */
 } vb200_epilogue;
 
-/* OR-ed into the epilogue argument of vb200_gemm_bf16: use the small-footprint tiling (256 TMEM
- * columns, ~130 KB shared memory per CTA) so that the launch can share every SM with one CTA of a
- * concurrent vb200_flash_attn_varlen launch on another stream (the attention of the other half of
- * the batch; see engine.InterleavedSession).  Results are bit-identical to the default tiling. */
-enum { VB200_GEMM_COSCHEDULE = 256 };
-
 typedef enum { VB200_ABSORBING = 0, VB200_UNIFORM = 1 } vb200_transition;
 
 typedef enum {

@@ -33,25 +33,18 @@ constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 //           measured necessary: a lone CTA sustains 163 cycles per 128x256x16 MMA against 128 nominal.
 // CTAS = 1, BN = 128: narrow tiles for problems with fewer 128x256 tiles than SMs (one utterance
 //           at a time: M ~ 1000) — twice the CTAs, 32 KB stages, 6 stages.
-// LITE (CTA pair only): a footprint that leaves room for ONE attention CTA on the same SM (attention:
-//           256 TMEM columns, 82 KB) — 3 stages (96 KB) and a single 256-column accumulator, so the
-//           tile's epilogue is not hidden behind the next tile's MMAs; meant for running next to the
-//           attention of the other half of the batch (engine.InterleavedSession), whose MMAs and
-//           softmax fill the gaps.
-template <int CTAS, int BN, bool LITE = false> struct Cfg {
+template <int CTAS, int BN> struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = LITE ? 3 : (4 * 48 * 1024) / STAGE_BYTES;   // 4 x 48 KB, 6 x 32 KB, 8 x 24 KB
-  static constexpr int NACC = LITE ? 1 : 2;                                 // accumulator buffers in TMEM
-  static constexpr uint32_t TMEM_COLS = LITE ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 8 * 32 * 128 + 1024 + 256;
+  static constexpr int STAGES = (4 * 48 * 1024) / STAGE_BYTES;   // 4 x 48 KB, 6 x 32 KB, 8 x 24 KB
 };
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;   // 320
 constexpr int EPI_TILE_BYTES = 32 * 128;        // 32 rows x 128 B per epilogue warp
 constexpr int SMEM_BYTES = 4 * 48 * 1024 + EPI_WARPS * EPI_TILE_BYTES + 1024 /*align slack*/ +
                            256 /*barriers*/;     // 4 x 48 KB == 6 x 32 KB
+constexpr uint32_t TMEM_COLS = 512;
 }  // namespace gemm
 
 // gelu(x) = 0.5 x (1 + erf(x / sqrt 2)) = x * (x > 0 ? 1 - q : q),  q(z) = 0.5 erfc(z),  z = |x| / sqrt 2.
@@ -82,14 +75,13 @@ __device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
   unpack2(ffma2(pack2(x0, x1), s, 0ull), x0, x1);
 }
 
-template <int EPI, typename OutT, int CTAS, int BN, bool LITE = false>
+template <int EPI, typename OutT, int CTAS, int BN>
 __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
     const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N, int K) {
   using namespace gemm;
-  using C = Cfg<CTAS, BN, LITE>;
-  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_ROWS = C::B_ROWS, NACC = C::NACC;
-  constexpr uint32_t TMEM_COLS = C::TMEM_COLS;
+  using C = Cfg<CTAS, BN>;
+  constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_ROWS = C::B_ROWS;
   constexpr int HALF_COLS = BN / 2;            // accumulator columns per epilogue warp
   const uint32_t cta_rank = CTAS == 2 ? cluster_ctarank() : 0;       // 0 = leader of the pair
   extern __shared__ uint8_t smem_raw[];
@@ -197,8 +189,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
-        const int as = NACC == 2 ? (it & 1) : 0;
-        const uint32_t aphase = NACC == 2 ? ((it >> 1) & 1) : (it & 1);
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&acc_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -241,8 +233,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
       const int m_blk = tile / num_n, n_blk = tile % num_n;
-      const int as = NACC == 2 ? (it & 1) : 0;
-      const uint32_t aphase = NACC == 2 ? ((it >> 1) & 1) : (it & 1);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const int row0 = (m_blk * CTAS + cta_rank) * BM + quad * 32;
@@ -329,7 +321,7 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
 // ---------------------------------------------------------------- host side
 template <int EPI, typename OutT>
 static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, const float* bias, int M, int N,
-                       int K, bool lite, cudaStream_t st) {
+                       int K, cudaStream_t st) {
   using namespace gemm;
   // Four tilings, picked by estimated cycles = waves x k-steps x cycles per MMA (tools/mma_bench.cu):
   //   CTA pair 256x256 (~135 cycles per k-step, half as many schedulable units, + ~5 000 cycles per
@@ -402,15 +394,6 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
       configured = true;
     }
     VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K));
-  } else if (lite) {
-    auto kern = gemm_tcgen05_kernel<EPI, OutT, 2, 256, true>;
-    constexpr int kSmem = Cfg<2, 256, true>::SMEM_BYTES;
-    static bool configured = false;
-    if (!configured) {
-      VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-      configured = true;
-    }
-    VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), kSmem, st, 2, ta, tb, tout, bias, M, N, K));
   } else {
     auto kern = gemm_tcgen05_kernel<EPI, OutT, 2, 256>;
     static bool configured = false;
@@ -426,11 +409,11 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
 
 template <int EPI>
 static int launch_gemm_dtype(void* out, vb200_dtype dt, const void* A, const void* W, const float* bias, int M,
-                             int N, int K, bool lite, cudaStream_t st) {
+                             int N, int K, cudaStream_t st) {
   switch (dt) {
-    case VB200_F32: return launch_gemm<EPI, float>(out, dt, A, W, bias, M, N, K, lite, st);
-    case VB200_BF16: return launch_gemm<EPI, __nv_bfloat16>(out, dt, A, W, bias, M, N, K, lite, st);
-    case VB200_F16: return launch_gemm<EPI, __half>(out, dt, A, W, bias, M, N, K, lite, st);
+    case VB200_F32: return launch_gemm<EPI, float>(out, dt, A, W, bias, M, N, K, st);
+    case VB200_BF16: return launch_gemm<EPI, __nv_bfloat16>(out, dt, A, W, bias, M, N, K, st);
+    case VB200_F16: return launch_gemm<EPI, __half>(out, dt, A, W, bias, M, N, K, st);
   }
   set_error("gemm: unknown out dtype %d", static_cast<int>(dt));
   return VB200_ERR_INVALID;
@@ -442,9 +425,7 @@ using namespace vb200;
 
 extern "C" int vb200_gemm_bf16(void* out, vb200_dtype out_dtype, const void* A, const void* W,
                                const float* bias, const float* residual, int32_t M, int32_t N,
-                               int32_t K, vb200_epilogue epi_flags, vb200_stream_t stream) {
-  const bool lite = (static_cast<int>(epi_flags) & VB200_GEMM_COSCHEDULE) != 0;
-  const vb200_epilogue epi = static_cast<vb200_epilogue>(static_cast<int>(epi_flags) & ~VB200_GEMM_COSCHEDULE);
+                               int32_t K, vb200_epilogue epi, vb200_stream_t stream) {
   VB_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad sizes M=%d N=%d K=%d", M, N, K);
   if (M == 0) return VB200_OK;                    // nothing to do (empty tensors carry null pointers)
   VB_REQUIRE(out && A && W, "gemm: null pointer");
@@ -456,15 +437,15 @@ extern "C" int vb200_gemm_bf16(void* out, vb200_dtype out_dtype, const void* A, 
              "gemm: BIAS_RESIDUAL needs residual and fp32 output");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epi) {
-    case VB200_EPI_NONE: return launch_gemm_dtype<VB200_EPI_NONE>(out, out_dtype, A, W, bias, M, N, K, lite, st);
-    case VB200_EPI_BIAS: return launch_gemm_dtype<VB200_EPI_BIAS>(out, out_dtype, A, W, bias, M, N, K, lite, st);
-    case VB200_EPI_BIAS_GELU: return launch_gemm_dtype<VB200_EPI_BIAS_GELU>(out, out_dtype, A, W, bias, M, N, K, lite, st);
+    case VB200_EPI_NONE: return launch_gemm_dtype<VB200_EPI_NONE>(out, out_dtype, A, W, bias, M, N, K, st);
+    case VB200_EPI_BIAS: return launch_gemm_dtype<VB200_EPI_BIAS>(out, out_dtype, A, W, bias, M, N, K, st);
+    case VB200_EPI_BIAS_GELU: return launch_gemm_dtype<VB200_EPI_BIAS_GELU>(out, out_dtype, A, W, bias, M, N, K, st);
     case VB200_EPI_BIAS_RESIDUAL:
       // out (+)= acc + bias is a TMA reduce-add into `out`; a distinct residual is copied in first
       if (residual != static_cast<const float*>(out))
         VB_CHECK_CUDA(cudaMemcpyAsync(out, residual, static_cast<size_t>(M) * N * sizeof(float),
                                       cudaMemcpyDeviceToDevice, st));
-      return launch_gemm<VB200_EPI_BIAS_RESIDUAL, float>(out, out_dtype, A, W, bias, M, N, K, lite, st);
+      return launch_gemm<VB200_EPI_BIAS_RESIDUAL, float>(out, out_dtype, A, W, bias, M, N, K, st);
   }
   set_error("gemm: unknown epilogue %d", static_cast<int>(epi));
   return VB200_ERR_INVALID;

@@ -185,8 +185,7 @@ class DenoiserEngine:
 
     # ------------------------------------------------------------------ one denoiser forward
     def forward(self, lay: BatchLayout, ws: Workspace, resp_ids: torch.Tensor, level_utt: torch.Tensor,
-                use_time: bool, hidden_out: list | None = None, head: bool = True,
-                cosched: bool = False) -> torch.Tensor:
+                use_time: bool, hidden_out: list | None = None, head: bool = True) -> torch.Tensor:
         """resp_ids int32 (M_resp, levels_in); level_utt int32 (B) = AdaLN row (and time_emb row when
         use_time).  Returns ws.logits (M_resp, n_out): classifier(x) on the response rows."""
         w = self.w
@@ -196,10 +195,7 @@ class DenoiserEngine:
                        w.ensure_pe(lay.max_T), lay.text_ids, lay.prom_ids, resp_ids, lay.utt, lay.row_utt,
                        level_utt, w.K, levels_in)
         scale = 64 ** -0.5
-        attn_flops = sum(4 * T * T * w.d for T in lay.rows)
-
-        def gemm(*a, **k):      # cosched: tiling that leaves room for the other half's attention CTAs
-            return self._gemm(*a, cosched=cosched, **k)
+        gemm, attn_flops = self._gemm, sum(4 * T * T * w.d for T in lay.rows)
         for ly in w.layers:
             self._norm(ws.h, ws.x, ly["norm_attn"], level_utt, lay)
             gemm(ws.qkv, ws.h, ly["w_qkv"], epi=L.EPI_NONE)
@@ -221,9 +217,9 @@ class DenoiserEngine:
         self.launches += 1
         return ws.logits
 
-    def _gemm(self, out, A, W, bias=None, residual=None, epi=L.EPI_NONE, cosched=False):
+    def _gemm(self, out, A, W, bias=None, residual=None, epi=L.EPI_NONE):
         ev = self._prof_begin()
-        L.gemm_bf16(out, A, W, bias, residual=residual, epi=epi, simt=self.simt, cosched=cosched)
+        L.gemm_bf16(out, A, W, bias, residual=residual, epi=epi, simt=self.simt)
         self._prof_end(ev, "gemm", 2 * A.shape[0] * A.shape[1] * W.shape[0])
 
     def _prof_begin(self):
@@ -269,9 +265,8 @@ class Session:
     captured graph is replayed unchanged."""
 
     def __init__(self, engine: DenoiserEngine, lay: BatchLayout, ws: Workspace | None = None,
-                 x_t: torch.Tensor | None = None, n_levels: int = 8, cosched: bool = False):
+                 x_t: torch.Tensor | None = None, n_levels: int = 8):
         self.eng, self.lay = engine, lay
-        self.cosched = cosched
         dev = engine.w.device
         self.ws = ws if ws is not None else engine.workspace(lay)
         self.x_t = x_t if x_t is not None else torch.empty(lay.M_resp, n_levels, dtype=torch.int32, device=dev)
@@ -313,7 +308,7 @@ class Session:
 
         def one_step(uniforms=None):
             if eng.profile is None and not eng.simt:
-                head_in = eng.forward(lay, ws, x_t, t_utt, use_time=True, head=False, cosched=self.cosched)
+                head_in = eng.forward(lay, ws, x_t, t_utt, use_time=True, head=False)
                 L.head_posterior_sample(x_t, ws.logits, head_in, w.w_cls, w.b_cls, x_t, lay.resp_row_utt, t_utt,
                                         lay.utt, table, n_levels, K, transition, noise, uniforms, seed)
                 eng.launches += 0 if L.head_fused(w.d, K, noise) else 1   # the `+= 2` below counts one of them
@@ -355,52 +350,3 @@ class Session:
             self.graph.replay()
             eng.launches += self.per_step_launches
         return x_t
-
-
-class InterleavedSession:
-    """Two half-batch Sessions on two CUDA streams, so that the attention of one half (issue-bound:
-    tensor pipe ~30 % busy) runs on the same SMs as the GEMMs of the other half (tensor-bound, few
-    issue slots).  Utterances are independent, so splitting the batch changes nothing in the
-    results: codes are bit-identical to one Session over the whole batch.  The GEMMs use the
-    small-footprint tiling (VB200_GEMM_COSCHEDULE) that leaves room for one attention CTA per SM;
-    two GEMM launches cannot share an SM, so the streams fall into an alternating schedule by
-    themselves.  Same interface as Session for what the callers use (load / run / x_t)."""
-
-    def __init__(self, engine: DenoiserEngine, text_list, proms_list, resp_lens, gids=None, n_levels: int = 8):
-        dev = engine.w.device
-        B = len(text_list)
-        if B < 2:
-            raise ValueError("an interleaved session needs at least two utterances")
-        gids = list(range(B)) if gids is None else list(gids)
-        rows = [len(t) + 1 + len(p) + 1 + int(r) for t, p, r in zip(text_list, proms_list, resp_lens)]
-        cost = np.cumsum([24 * T * engine.w.d ** 2 + 4 * T * T * engine.w.d for T in rows], dtype=np.float64)
-        cut = int(np.searchsorted(cost, cost[-1] / 2)) + 1          # contiguous halves of about equal cost
-        self.cut = cut = min(max(cut, 1), B - 1)
-        self.eng, self.B = engine, B
-        self.t_resp = [int(r) for r in resp_lens]
-        self.M_resp = sum(self.t_resp)
-        self.x_t = torch.empty(self.M_resp, n_levels, dtype=torch.int32, device=dev)
-        m0 = sum(self.t_resp[:cut])
-        self.halves = []
-        for sl, xs in ((slice(0, cut), self.x_t[:m0]), (slice(cut, B), self.x_t[m0:])):
-            lay = BatchLayout(text_list[sl], proms_list[sl], resp_lens[sl], dev, gids=gids[sl])
-            self.halves.append(Session(engine, lay, x_t=xs, n_levels=n_levels, cosched=True))
-        self.streams = [torch.cuda.Stream(device=dev) for _ in self.halves]
-        self.h2d_bytes = sum(h.lay.h2d_bytes for h in self.halves)
-
-    def load(self, text_list, proms_list, gids=None) -> int:
-        c = self.cut
-        g = list(range(self.B)) if gids is None else list(gids)
-        return (self.halves[0].load(text_list[:c], proms_list[:c], g[:c]) +
-                self.halves[1].load(text_list[c:], proms_list[c:], g[c:]))
-
-    def run(self, table, timesteps, transition, noise=L.NOISE_PHILOX, seed=0, n_levels: int = 8) -> torch.Tensor:
-        dev = self.eng.w.device
-        cur = torch.cuda.current_stream(dev)
-        for st, h in zip(self.streams, self.halves):
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                h.run(table, timesteps, transition, noise=noise, seed=seed, use_graph=True, n_levels=n_levels)
-        for st in self.streams:
-            cur.wait_stream(st)
-        return self.x_t

@@ -17,7 +17,6 @@ LIB_PATH = Path(os.environ.get("VB200_LIB", _HERE / "libvalle_b200.so"))   # ove
 OK = 0
 F32, BF16, F16 = 0, 1, 2
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RESIDUAL = 0, 1, 2, 3
-GEMM_COSCHEDULE = 0x100
 ABSORBING, UNIFORM = 0, 1
 NOISE_PHILOX, NOISE_UNIFORMS, NOISE_GREEDY = 0, 1, 2
 U_ROW0, U_TTXT, U_TPROM, U_TRESP, U_TXT0, U_PROM0, U_RESP0, U_GID, U_STRIDE = range(9)
@@ -143,10 +142,7 @@ def codes_to_bqt(out, codes, utt, pad=0):
            "vb200_codes_to_bqt")
 
 
-def gemm_bf16(out, A, W, bias=None, residual=None, epi=EPI_NONE, simt=False, cosched=False):
-    """``cosched``: small-footprint tiling (VB200_GEMM_COSCHEDULE) that shares an SM with an attention CTA."""
-    if cosched and not simt:
-        epi |= GEMM_COSCHEDULE
+def gemm_bf16(out, A, W, bias=None, residual=None, epi=EPI_NONE, simt=False):
     M, K = A.shape
     N = W.shape[0]
     assert W.shape[1] == K and tuple(out.shape) == (M, N), (A.shape, W.shape, out.shape)
