@@ -16,7 +16,7 @@ omegaconf, and ``ar_discrete.py:14,16`` import diffusers/timm, which are stubbed
 * runs the reference ``Base`` stack (``base.py``) in NAR configuration on a small model.
 
 Outputs (small, committed): d3pm_absorbing_k1025.npz, d3pm_uniform_k1025.npz,
-d3pm_small_*.npz, denoiser_nar_small.npz, denoiser_diffusion_small.npz
+d3pm_small_*.npz, denoiser_nar_small.npz, denoiser_diffusion_small.npz, ar_discrete_dit.npz
 """
 import importlib.util
 import sys
@@ -33,14 +33,32 @@ REF = Path("/root/reference/vall_e/vall_e")
 OUT = Path(__file__).resolve().parent
 
 
+class TimmLikeMlp(torch.nn.Module):
+    """Stand-in for ``timm.models.vision_transformer.Mlp`` (timm is not installed here): the same
+    sub-module names and order — fc1, act, drop1, norm (Identity), fc2, drop2 — and forward."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=torch.nn.GELU, drop=0.0):
+        super().__init__()
+        self.fc1 = torch.nn.Linear(in_features, hidden_features or in_features)
+        self.act = act_layer()
+        self.drop1 = torch.nn.Dropout(drop)
+        self.norm = torch.nn.Identity()
+        self.fc2 = torch.nn.Linear(hidden_features or in_features, out_features or in_features)
+        self.drop2 = torch.nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop2(self.fc2(self.norm(self.drop1(self.act(self.fc1(x))))))
+
+
 def load_reference():
     diffusers = types.ModuleType("diffusers")
     for n in ("UNet3DConditionModel", "UNet2DConditionModel", "DDPMScheduler",
               "CosineDPMSolverMultistepScheduler", "DDIMScheduler"):
         setattr(diffusers, n, object)
     tv = types.ModuleType("timm.models.vision_transformer")
-    for n in ("PatchEmbed", "Attention", "Mlp"):
+    for n in ("PatchEmbed", "Attention"):
         setattr(tv, n, object)
+    tv.Mlp = TimmLikeMlp        # the reference instantiates timm's Mlp (ar_discrete.py:124,227,235)
     sys.modules.update({"diffusers": diffusers, "timm": types.ModuleType("timm"),
                         "timm.models": types.ModuleType("timm.models"),
                         "timm.models.vision_transformer": tv})
@@ -239,9 +257,72 @@ def gen_denoiser(mods, seed=7):
     print("denoiser fixtures written; state-dict keys:", len(sd))
 
 
+def det_state_dict(shapes, seed=4242):
+    """Deterministic weights for the compat DiT, regenerated identically by the test (detrand)."""
+    sd = {}
+    for i, (k, shape) in enumerate(sorted(shapes.items())):
+        v = detrand.normal(seed + 17 * i, tuple(shape)) * np.float32(0.1)
+        if k.endswith("weight") and len(shape) == 1:          # LayerNorm gains around 1
+            v = v + np.float32(1.0)
+        sd[k] = torch.from_numpy(v.astype(np.float32))
+    return sd
+
+
+def gen_ar_discrete_dit(mods, seed=99):
+    """The reference's own D3PM class (ar_discrete.py:205-256): denoiser logits for one timestep and
+    the two conditioning encodings, computed by the reference's modules with the call sequence of
+    its generate_audio (:735-776; the method itself hard-codes cuda:0).  The constructor moves its
+    tables to cuda:0 and chains 99 (1025, 1025) fp16 products — both neutralised while it runs."""
+    ar = mods["ar_discrete"]
+    real_to, real_td = torch.Tensor.to, torch.tensordot
+
+    def cpu_to(self, *a, **k):
+        a = tuple(x for x in a if not (isinstance(x, str) and x.startswith("cuda")))
+        return real_to(self, *a, **k) if (a or k) else self
+    torch.Tensor.to, torch.tensordot = cpu_to, (lambda a, b, dims=None: a)
+    try:
+        m = ar.AR(32, 100, 1025, 8, 16, 8)
+    finally:
+        torch.Tensor.to, torch.tensordot = real_to, real_td
+    m.eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    m.load_state_dict(det_state_dict(shapes))
+    text = torch.from_numpy(detrand.integers(seed, 1, 1025, (37,)))
+    proms = torch.from_numpy(detrand.integers(seed + 1, 0, 1025, (180, 8)))
+    x_t = torch.zeros(1, 448, dtype=torch.int32)
+    x_t[0, :350] = torch.from_numpy(detrand.integers(seed + 2, 1, 1025, (350,))).int()
+    t = torch.tensor([40])
+    F = torch.nn.functional
+    with torch.no_grad():
+        mask = x_t[0] != 0                                                   # :712
+        text_p = torch.stack([F.pad(text, (0, 50 - text.shape[0]))])        # :715-721
+        proms_p = torch.stack([F.pad(proms, (0, 0, 0, 398 - proms.shape[0]))])   # :723-735
+        cond1 = m.proms_emb(torch.stack([p[:398, :] for p in proms_p]))[0]  # :736-737
+        cond2 = m.text_emb(text_p)                                           # :739
+        cond2 = m.sin_emb.add_pe(cond2)[0]
+        cond2 = m.encodertext(cond2).unsqueeze(0)
+        cond1 = m.sin_emb.add_pe(cond1)[0]
+        cond1 = m.encoder2(cond1).unsqueeze(0)
+        t_emb = m.time_emb(t)                                                # :752
+        x = m.resps_emb(x_t)[0].unsqueeze(0)                                 # :753,760
+        for block in m.blocks:
+            x = block(x, cond1, cond2, t_emb, mask)
+        x = x[:448, :] * mask.unsqueeze(1)                                   # :772
+        logits = m.final(x)
+    rows = np.array([0, 1, 2, 100, 200, 349, 350, 447])
+    np.savez_compressed(OUT / "ar_discrete_dit.npz", keys=np.array(sorted(shapes)),
+                        shapes=np.array([str(shapes[k]) for k in sorted(shapes)]),
+                        rows=rows, logits_rows=logits[0, rows].numpy(), logits_absmax=float(logits.abs().max()),
+                        logits_sum=float(logits.double().sum()), cond1_head=cond1[0, :4].numpy(),
+                        cond2_head=cond2[0, :4].numpy(), seed=seed, t=40)
+    print("ar_discrete DiT fixture written:", len(shapes), "state-dict entries, logits", tuple(logits.shape),
+          "absmax", float(logits.abs().max()))
+
+
 if __name__ == "__main__":
     mods = load_reference()
     AR = mods["ar_discrete"].AR
     gen_d3pm(AR, "absorbing")
     gen_d3pm(AR, "uniform")
     gen_denoiser(mods)
+    gen_ar_discrete_dit(mods)

@@ -398,3 +398,43 @@ def test_encodec_handoff_bqt_layout_matches_reference_rearrange():
         assert torch.equal(out.cpu(), ref)
     L.codes_to_bqt(torch.empty(0, 8, 4, dtype=torch.int64, device=DEV), torch.empty(0, 8, dtype=torch.int32, device=DEV),
                    torch.empty(0, L.U_STRIDE, dtype=torch.int32, device=DEV))
+
+
+def test_ar_discrete_compat_reverse_step_and_loop(golden_dir):
+    """the drop-in for the reference's own D3PM class (K = 1025, level 0, d = 32 DiT).
+    Denoiser logits on the GPU agree with the reference fixture; one reverse step on those logits
+    agrees with the oracle's dense fp16-table p_sample (supplied uniforms and greedy, wherever the
+    reference's top-2 margin is clear); the 99-step loop runs, is seed-reproducible, and returns the
+    reference's (448,) layout."""
+    import detrand
+    from oracle.d3pm import D3PM
+    from test_host_cpu import _compat_dit
+    m, z, _, text, proms, x_t = _compat_dit(golden_dir)
+    m = m.to(DEV)
+    t = torch.tensor([int(z["t"])], device=DEV)
+    with torch.no_grad():
+        cond1, cond2 = m.conditioning(text.to(DEV), proms.to(DEV))
+        logits = m.denoise_logits(x_t.to(DEV), t, cond1, cond2, (x_t[0] != 0).to(DEV))
+    err = np.abs(logits[0, torch.from_numpy(z["rows"]).to(DEV)].cpu().numpy() - z["logits_rows"]).max()
+    assert err <= 2e-3, err                    # fp32 (TF32 off) PyTorch modules; fp16 sin/cos tables differ in the last bit
+    orc = D3PM(100, 1025, "absorbing")
+    noise = torch.from_numpy(detrand.uniform(5, (1, 448, 1025)))
+    lg16 = logits.cpu().to(torch.float16)
+    ref_samp, ref_post = orc.p_sample(lg16, t.cpu(), x_t, noise)
+    ref_greedy, _ = orc.p_sample(lg16, t.cpu(), x_t, greedy=True)
+    got, probs = m.p_sample(logits, t, x_t.to(DEV), noise=noise.to(DEV))
+    greedy, _ = m.p_sample(logits, t, x_t.to(DEV), greedy=True)
+    assert got.shape == (1, 448) and probs.shape == (1, 448, 1025)
+    g = -torch.log(-torch.log(noise.clamp(min=torch.finfo(torch.float32).tiny)))
+    top2 = (ref_post.float() + g).topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 0.05
+    assert clear.float().mean().item() > 0.8
+    assert torch.equal(got.cpu()[clear], ref_samp[clear])
+    top2 = ref_post.float().topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 0.05
+    assert torch.equal(greedy.cpu()[clear], ref_greedy[clear])
+    a = m.generate_audio([text.to(DEV)], [proms.to(DEV)], seed=7)
+    b = m.generate_audio([text.to(DEV)], [proms.to(DEV)], seed=7)
+    c = m.generate_audio([text.to(DEV)], [proms.to(DEV)], seed=8)
+    assert a.shape == (448,) and a.dtype == torch.int64 and int(a.min()) >= 0 and int(a.max()) < 1025
+    assert torch.equal(a, b) and not torch.equal(a, c)

@@ -229,3 +229,46 @@ def test_sharded_generation_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _compat_dit(golden_dir):
+    import detrand
+    from vall_e.vall_e.ar_discrete import AR
+    z = np.load(golden_dir / "ar_discrete_dit.npz")
+    m = AR(32, 100, 1025, 8, 16, 8).eval()
+    shapes = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    sd = {}
+    for i, (k, shape) in enumerate(sorted(shapes.items())):     # same recipe as make_golden.det_state_dict
+        v = detrand.normal(4242 + 17 * i, tuple(shape)) * np.float32(0.1)
+        if k.endswith("weight") and len(shape) == 1:
+            v = v + np.float32(1.0)
+        sd[k] = torch.from_numpy(v.astype(np.float32))
+    m.load_state_dict(sd)
+    seed = int(z["seed"])
+    text = torch.from_numpy(detrand.integers(seed, 1, 1025, (37,)))
+    proms = torch.from_numpy(detrand.integers(seed + 1, 0, 1025, (180, 8)))
+    x_t = torch.zeros(1, 448, dtype=torch.int32)
+    x_t[0, :350] = torch.from_numpy(detrand.integers(seed + 2, 1, 1025, (350,))).int()
+    return m, z, shapes, text, proms, x_t
+
+
+def test_ar_discrete_compat_matches_reference_module(golden_dir):
+    """the drop-in for the reference's own D3PM class (ar_discrete.py:205-256) has the
+    reference's state-dict keys and shapes, and its conditioning encoders and DiT denoiser reproduce
+    the reference modules' outputs (fixture written by make_golden.gen_ar_discrete_dit)."""
+    m, z, shapes, text, proms, x_t = _compat_dit(golden_dir)
+    assert sorted(shapes) == [str(k) for k in z["keys"]]
+    assert [str(shapes[k]) for k in sorted(shapes)] == [str(s) for s in z["shapes"]]
+    with torch.no_grad():
+        cond1, cond2 = m.conditioning(text, proms)
+        logits = m.denoise_logits(x_t, torch.tensor([int(z["t"])]), cond1, cond2, x_t[0] != 0)
+    assert cond1.shape == (1, 398, 32) and cond2.shape == (1, 50, 32) and logits.shape == (1, 448, 1025)
+    assert np.abs(cond1[0, :4].numpy() - z["cond1_head"]).max() <= 1e-5
+    assert np.abs(cond2[0, :4].numpy() - z["cond2_head"]).max() <= 1e-5
+    err = np.abs(logits[0, z["rows"]].numpy() - z["logits_rows"]).max()
+    assert err <= 1e-4, err                               # fp32 PyTorch modules on both sides
+    assert abs(float(logits.double().sum()) - float(z["logits_sum"])) <= 1e-2 * 448
+    # D3PM constants of the class: K = 1025, absorbing class 512, 100 timesteps (ar_discrete.py:207,255,332)
+    assert (m.num_classes, m.mask_id, m.timesteps, m.transition) == (1025, 512, 100, "absorbing")
+    with pytest.raises(ValueError):
+        m.generate_audio([text, text], [proms, proms])

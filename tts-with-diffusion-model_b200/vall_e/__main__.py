@@ -8,8 +8,9 @@ entry point needs the reference's ``vall_e.emb`` (encodec, g2p_en, soundfile) im
 checkpoints are whole-module pickles (reference ``export.py``) resolved through this package's
 ``vall_e.vall_e.{ar,nar,diffusion}`` classes.
 
-  --ar-ckpt may hold a ``Diffusion`` model (8 levels in one reverse loop; NAR is then skipped) or a
-  reference AR model (unsupported here: raises).
+  --ar-ckpt may hold a ``Diffusion`` model (8 levels in one reverse loop; NAR is then skipped), the
+  reference's own level-0 D3PM class (``vall_e.vall_e.ar_discrete.AR``: 350 frames by diffusion, then
+  the NAR pass), or a reference causal AR model (unsupported here: raises).
 """
 import argparse
 from pathlib import Path
@@ -18,6 +19,7 @@ import torch
 from einops import rearrange
 
 from .utils import to_device
+from .vall_e.ar_discrete import AR as DiscreteAR
 from .vall_e.diffusion import Diffusion
 
 
@@ -68,7 +70,10 @@ def main():
         resps_list = first.generate_audio(text_list=[phns], proms_list=[proms], resp_lens=lens, seed=args.seed)
     else:
         nar = _load(args.nar_ckpt, args.device)
-        resp_list = first(text_list=[phns], proms_list=[proms])
+        if isinstance(first, DiscreteAR):       # the reference's own D3PM class: level 0 by diffusion, 350 frames
+            resp_list = [first.generate_audio([phns], [proms], seed=args.seed)[:350]]
+        else:
+            resp_list = first(text_list=[phns], proms_list=[proms])
         resps_list = [r.unsqueeze(-1) for r in resp_list]
         resps_list = nar(text_list=[phns], proms_list=[proms], resps_list=resps_list)
     qnt.decode_to_file(resps=resps_list[0], path=args.out_path)

@@ -24,48 +24,10 @@ from .base import Base
 _TRANSITIONS = {"absorbing": L.ABSORBING, "uniform": L.UNIFORM}
 
 
-class Diffusion(Base):
-    n_levels = 8  # codebooks diffused jointly (EnCodec 6 kbps, emb/qnt.py:21-23)
-
-    @property
-    def n_resp_levels(self):
-        return 8
-
-    @property
-    def casual(self):
-        return False
-
-    @property
-    def use_stop_token(self):
-        return False
-
-    @property
-    def norm_type(self):
-        return "adaln"
-
-    @property
-    def resp_loss_only(self):
-        return True
-
-    @property
-    def n_norm_levels(self):
-        return self.timesteps + 1
-
-    def _n_classifier_out(self, n_resp_tokens):
-        return self.n_levels * n_resp_tokens
-
-    def __init__(self, n_tokens: int = 1024, d_model: int = 1024, n_heads: int = 16, n_layers: int = 12,
-                 p_dropout: float = 0.1, n_steps: int = 50, transition: str = "absorbing"):
-        if transition not in _TRANSITIONS:
-            raise ValueError(f"transition must be 'absorbing' or 'uniform', got {transition!r}")
-        # attributes the constructor of Base reads through the properties above
-        nn.Module.__init__(self)
-        self.timesteps = int(n_steps)
-        self.transition = transition
-        super().__init__(n_tokens, d_model=d_model, n_heads=n_heads, n_layers=n_layers, p_dropout=p_dropout)
-        self.time_emb = nn.Embedding(self.timesteps + 1, d_model)
-        self.num_classes = n_tokens
-        self.eps = d3pm.EPS
+class D3PMOps:
+    """The D3PM algebra of ``ar_discrete.py`` on the B200 kernels, for any module that defines
+    ``num_classes``, ``timesteps`` and ``transition``: schedule / table access, ``q_sample``,
+    ``q_posterior_logits`` and ``p_sample`` with the reference's signatures and shapes."""
 
     # ------------------------------------------------------------------ D3PM constants
     @property
@@ -150,6 +112,50 @@ class Diffusion(Base):
                 noise = torch.rand(size=x.shape + (self.num_classes,)).to(x.device)
         sample, _ = self._posterior(model_logits, t, x, mode, noise, want_post=False, seed=seed or 0)
         return sample, F.softmax(model_logits, dim=-1)
+
+
+class Diffusion(D3PMOps, Base):
+    n_levels = 8  # codebooks diffused jointly (EnCodec 6 kbps, emb/qnt.py:21-23)
+
+    @property
+    def n_resp_levels(self):
+        return 8
+
+    @property
+    def casual(self):
+        return False
+
+    @property
+    def use_stop_token(self):
+        return False
+
+    @property
+    def norm_type(self):
+        return "adaln"
+
+    @property
+    def resp_loss_only(self):
+        return True
+
+    @property
+    def n_norm_levels(self):
+        return self.timesteps + 1
+
+    def _n_classifier_out(self, n_resp_tokens):
+        return self.n_levels * n_resp_tokens
+
+    def __init__(self, n_tokens: int = 1024, d_model: int = 1024, n_heads: int = 16, n_layers: int = 12,
+                 p_dropout: float = 0.1, n_steps: int = 50, transition: str = "absorbing"):
+        if transition not in _TRANSITIONS:
+            raise ValueError(f"transition must be 'absorbing' or 'uniform', got {transition!r}")
+        # attributes the constructor of Base reads through the properties above
+        nn.Module.__init__(self)
+        self.timesteps = int(n_steps)
+        self.transition = transition
+        super().__init__(n_tokens, d_model=d_model, n_heads=n_heads, n_layers=n_layers, p_dropout=p_dropout)
+        self.time_emb = nn.Embedding(self.timesteps + 1, d_model)
+        self.num_classes = n_tokens
+        self.eps = d3pm.EPS
 
     # ------------------------------------------------------------------ denoiser logits
     def denoise_logits(self, text_list, proms_list, xt_list, t: Tensor, logits_dtype=torch.float32):
