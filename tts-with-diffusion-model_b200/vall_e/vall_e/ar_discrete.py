@@ -119,9 +119,11 @@ class AR(D3PMOps, nn.Module):
         self.proms_emb = MultiEmbedding(max_n_levels, 1025, d)
         self.resps_emb = nn.Embedding(1025, d, padding_idx=0)
         self.time_emb = nn.Embedding(self.timesteps + 1, d)
-        self.encodertext = nn.Sequential(TransformerEncoder(TransformerEncoderLayer(d_model=d, nhead=16), num_layers=2),
+        self.encodertext = nn.Sequential(TransformerEncoder(TransformerEncoderLayer(d_model=d, nhead=16), num_layers=2,
+                                                            enable_nested_tensor=False),
                                          Mlp(d, d * 2, d, act_layer=nn.SiLU, drop=0.01))
-        self.encoder2 = nn.Sequential(TransformerEncoder(TransformerEncoderLayer(d_model=d, nhead=16), num_layers=2),
+        self.encoder2 = nn.Sequential(TransformerEncoder(TransformerEncoderLayer(d_model=d, nhead=16), num_layers=2,
+                                                            enable_nested_tensor=False),
                                       Mlp(d, d * 3, d, act_layer=nn.SiLU, drop=0.01))
         self.sin_emb = SinusodialEmbedding(d)
         self.sin_emb2 = SinusodialEmbedding(d)
