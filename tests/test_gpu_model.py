@@ -438,3 +438,19 @@ def test_ar_discrete_compat_reverse_step_and_loop(golden_dir):
     c = m.generate_audio([text.to(DEV)], [proms.to(DEV)], seed=8)
     assert a.shape == (448,) and a.dtype == torch.int64 and int(a.min()) >= 0 and int(a.max()) < 1025
     assert torch.equal(a, b) and not torch.equal(a, c)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_second_device_in_the_same_process():
+    """Kernel attributes (dynamic shared memory limits) are per device: a process that drives two GPUs
+    must get identical codes from both (one-process-per-GPU is the deployment, this is the guard)."""
+    K, d, h, nl, S = 64, 128, 2, 2, 8
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        with torch.cuda.device(dev):
+            m, _ = _make(K, d, h, nl, S, "absorbing", seed=4)
+            m = m.to(dev)
+            text, proms, _ = _batch(K, [(4, 10, 140), (6, 7, 301)], 9)
+            outs.append([c.cpu() for c in m.generate_audio([x.to(dev) for x in text], [x.to(dev) for x in proms],
+                                                            resp_lens=[140, 301], seed=3)])
+    assert all(torch.equal(a, b) for a, b in zip(*outs))

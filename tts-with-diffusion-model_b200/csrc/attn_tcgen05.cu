@@ -568,12 +568,17 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
   if (rc != VB200_OK) return rc;
   dim3 grid((max_T + BQ - 1) / BQ, n_heads, B);
   const float sl2 = scale * 1.4426950408889634f;
-  static bool configured = false;
-  if (!configured) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                       cudaSharedmemCarveoutMaxShared));   // two CTAs per SM
-    configured = true;
+  VB_CONFIGURE_SMEM(flash_attn_kernel, SMEM_BYTES);
+  {
+    static std::atomic<uint64_t> carveout_done{0};                         // per device, like the macro above
+    int dev = 0;
+    VB_CHECK_CUDA(cudaGetDevice(&dev));
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(carveout_done.load(std::memory_order_acquire) & bit)) {
+      VB_CHECK_CUDA(cudaFuncSetAttribute(flash_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));   // two CTAs per SM
+      carveout_done.fetch_or(bit, std::memory_order_release);
+    }
   }
   VB_CHECK_CUDA(launch_pdl(flash_attn_kernel, grid, dim3(THREADS), SMEM_BYTES, static_cast<cudaStream_t>(stream), 1,
                            tm, static_cast<__nv_bfloat16*>(out_bf16), cu_rows, n_heads, sl2));

@@ -1,6 +1,7 @@
 // Shared device/host helpers for libvalle_b200.so (sm_100a only).
 // Hand-written PTX wrappers for mbarrier, TMA (cp.async.bulk.tensor) and tcgen05/TMEM.
 #pragma once
+#include <atomic>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -46,6 +47,19 @@ int head_ce_fused(float* loss_out, const void* head_in, const void* W, const flo
 // kernel drains.  Valid under stream capture too.  Measured on B200 at batch 1 (89 kernels per
 // denoise step, graph replay): 0.878 ms with it, 0.861 ms without — the kernels of one step each
 // fill most SMs with CTAs of equal length, so there is no tail to overlap — hence off by default.
+// cudaFuncSetAttribute is per DEVICE: each launch site remembers which devices it has configured (a
+// process that drives several GPUs would otherwise launch with the 48 KB default on the second one).
+#define VB_CONFIGURE_SMEM(kern, bytes)                                                                   \
+  do {                                                                                                   \
+    static std::atomic<uint64_t> vb_cfg_done{0};                                                         \
+    int vb_cfg_dev = 0;                                                                                  \
+    VB_CHECK_CUDA(cudaGetDevice(&vb_cfg_dev));                                                           \
+    const uint64_t vb_cfg_bit = 1ull << (vb_cfg_dev & 63);                                               \
+    if (!(vb_cfg_done.load(std::memory_order_acquire) & vb_cfg_bit)) {                                   \
+      VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));     \
+      vb_cfg_done.fetch_or(vb_cfg_bit, std::memory_order_release);                                       \
+    }                                                                                                    \
+  } while (0)
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

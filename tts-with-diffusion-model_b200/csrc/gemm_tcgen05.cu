@@ -371,36 +371,20 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
   if (narrow64) {
     if constexpr (sizeof(OutT) == 4) {
       auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 64>;
-      static bool configured = false;
-      if (!configured) {
-        VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        configured = true;
-      }
+      VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
       VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K));
     }
   } else if (narrow) {
     auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 128>;
-    static bool configured = false;
-    if (!configured) {
-      VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      configured = true;
-    }
+    VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
     VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K));
   } else if (ctas == 1) {
     auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 256>;
-    static bool configured = false;
-    if (!configured) {
-      VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      configured = true;
-    }
+    VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
     VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K));
   } else {
     auto kern = gemm_tcgen05_kernel<EPI, OutT, 2, 256>;
-    static bool configured = false;
-    if (!configured) {
-      VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-      configured = true;
-    }
+    VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
     VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 2, ta, tb, tout, bias, M, N, K));
   }
   VB_CHECK_CUDA(cudaGetLastError());

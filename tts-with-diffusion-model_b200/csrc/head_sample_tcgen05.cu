@@ -391,11 +391,7 @@ static int launch_head_sample(int32_t* x_out, float* loss_out, const void* head_
   const int groups = num_sms() / 2;
   const int grid = (items < groups ? items : groups) * 2;
   auto kern = head_sample_kernel<NOISE>;
-  static bool configured = false;
-  if (!configured) {
-    VB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
-  }
+  VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
   VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 2, ta, tb, x_out, loss_out, bias, x_t, row_utt,
                            t_utt, utt, table, n_rows, n_levels, K, d, S, tr, static_cast<uint32_t>(seed),
                            static_cast<uint32_t>(seed >> 32)));
