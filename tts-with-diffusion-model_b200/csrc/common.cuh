@@ -47,6 +47,10 @@ int head_ce_fused(float* loss_out, const void* head_in, const void* W, const flo
 // kernel drains.  Valid under stream capture too.  Measured on B200 at batch 1 (89 kernels per
 // denoise step, graph replay): 0.878 ms with it, 0.861 ms without — the kernels of one step each
 // fill most SMs with CTAs of equal length, so there is no tail to overlap — hence off by default.
+// Re-measured with the final kernels: 832 us with it against 797 us without, and the same 832 us when the
+// GEMM / attention kernels trigger late (producer warp, after its last load) instead of at the top, so
+// it is not later kernels piling up on the SMs: replaying a graph with programmatic edges is simply
+// ~0.4 us per kernel slower here than plain stream order.
 // cudaFuncSetAttribute is per DEVICE: each launch site remembers which devices it has configured (a
 // process that drives several GPUs would otherwise launch with the 48 KB default on the second one).
 #define VB_CONFIGURE_SMEM(kern, bytes)                                                                   \
