@@ -87,31 +87,38 @@ int vb200_embed_gather(float* x_out, const void* text_w, const void* prom_w, con
                        int32_t M, int32_t d, int32_t K, int32_t resp_levels_in,
                        vb200_stream_t stream);
 
+/* 16-bit operands.  The two operands of a GEMM are both bf16 or both fp16 (`*_dtype` = VB200_BF16 |
+ * VB200_F16 names the dtype of the rows AND of the weights: tcgen05 kind::f16 faults on mixed formats).
+ * The engine keeps the normalised rows, the FFN hidden and the classifier input — and the weights they
+ * meet — in fp16 (11 significand bits against 8; conversions saturate at +-65504): with bf16 there the
+ * logits of the full model are 2.2e-2 off the fp32 reference, with fp16 5.5e-3; qkv, the
+ * attention output and the to_out weights stay bf16, and so do the embedding tables. */
+
 /* N1: AdaLN.forward (base.py:145-158): h = LN(x) (no affine, eps); h = c(1-k h)h;
  * y = gamma_l * h + beta_l with table (n_rows, 2d) fp32 = [exp(log gamma) | beta] (exp applied
- * once at weight-pack time).  Row l for utterance b is level_utt[b].  out bf16 (M, d). */
-int vb200_adaln(void* out_bf16, const float* x, const float* table, const int32_t* level_utt,
+ * once at weight-pack time).  Row l for utterance b is level_utt[b].  out (M, d) of out_dtype. */
+int vb200_adaln(void* out, vb200_dtype out_dtype, const float* x, const float* table, const int32_t* level_utt,
                 const int32_t* row_utt, int32_t M, int32_t d, float eps, float k, float c,
                 vb200_stream_t stream);
 
 /* N2 (norm_type == "ln"): nn.LayerNorm(d) with affine weight/bias (base.py:175-176). */
-int vb200_layernorm(void* out_bf16, const float* x, const float* weight, const float* bias,
+int vb200_layernorm(void* out, vb200_dtype out_dtype, const float* x, const float* weight, const float* bias,
                     int32_t M, int32_t d, float eps, vb200_stream_t stream);
 
-/* fp32 rows -> bf16 rows through an index (response rows for the classifier, base.py:443,491) */
-int vb200_gather_rows_bf16(void* out_bf16, const float* x, const int32_t* row_index,
+/* fp32 rows -> 16-bit rows through an index (response rows for the classifier, base.py:443,491) */
+int vb200_gather_rows_bf16(void* out, vb200_dtype out_dtype, const float* x, const int32_t* row_index,
                            int32_t n_rows, int32_t d, vb200_stream_t stream);
 
 /* A1/F1/H1 linear layers (base.py:110,129,209,214,355): out = epi(A[M,K] · W[N,K]ᵀ).
- * A, W bf16 row-major (nn.Linear weight layout); bias fp32 (N) or NULL; residual fp32 (M,N)
+ * A and W both bf16 or both fp16 (a_dtype), row-major (nn.Linear weight layout); bias fp32 (N) or NULL; residual fp32 (M,N)
  * (may alias out); out dtype per out_dtype (BIAS_RESIDUAL requires VB200_F32).
  * tcgen05 + TMEM + TMA kernel; requires K % 8 == 0, N % 8 == 0, 16-byte aligned pointers. */
-int vb200_gemm_bf16(void* out, vb200_dtype out_dtype, const void* A, const void* W,
+int vb200_gemm_bf16(void* out, vb200_dtype out_dtype, const void* A, vb200_dtype a_dtype, const void* W,
                     const float* bias, const float* residual, int32_t M, int32_t N, int32_t K,
                     vb200_epilogue epi, vb200_stream_t stream);
 
 /* Same contract, plain CUDA-core kernel.  Validation aid for tests / bring-up only. */
-int vb200_gemm_bf16_simt(void* out, vb200_dtype out_dtype, const void* A, const void* W,
+int vb200_gemm_bf16_simt(void* out, vb200_dtype out_dtype, const void* A, vb200_dtype a_dtype, const void* W,
                          const float* bias, const float* residual, int32_t M, int32_t N,
                          int32_t K, vb200_epilogue epi, vb200_stream_t stream);
 
@@ -178,7 +185,7 @@ int vb200_posterior_sample_from_logits(int32_t* x_out, float* post_out, const vo
                                        vb200_stream_t stream);
 
 /* H1 + P in one call (reference base.py:355,440 followed by
- * ar_discrete.py:347-375,401-420): logits = head_in (n_rows, d) bf16 x W (n_levels*K, d)^T + bias and
+ * ar_discrete.py:347-375,401-420): logits = head_in (n_rows, d) x W (n_levels*K, d)^T + bias (both bf16 or both fp16) and
  * the reverse step of vb200_posterior_sample_from_logits on them.
  * For K % 256 == 0 and noise != VB200_NOISE_UNIFORMS this is ONE kernel: the reverse step runs as
  * the GEMM's epilogue (streaming reservoir sampling over the column tiles of a level, see
@@ -188,8 +195,8 @@ int vb200_posterior_sample_from_logits(int32_t* x_out, float* post_out, const vo
  * differ (both are exact samples of the same posterior); greedy codes agree up to the fp16
  * rounding of the unfused logits. */
 int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_dtype logits_dtype,
-                                const void* head_in_bf16, const void* W_bf16, const float* bias,
-                                int32_t n_rows, int32_t d, int32_t n_levels, int32_t K,
+                                const void* head_in, vb200_dtype head_in_dtype, const void* W,
+                                const float* bias, int32_t n_rows, int32_t d, int32_t n_levels, int32_t K,
                                 const int32_t* x_t, const int32_t* row_utt, const int32_t* t_utt,
                                 const int32_t* utt, const float* table, int32_t S,
                                 vb200_transition tr, vb200_noise noise, const float* uniforms,
@@ -199,15 +206,16 @@ int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_dtype logits
  * classifier output): loss[r, l] = -log softmax(head_in[r] W_l^T + b_l)[targets[r, l]], float32
  * (n_rows, n_levels), computed as the classifier GEMM's epilogue (online log-sum-exp over the column
  * tiles of a level; no logits in HBM).  Needs K % 256 == 0. */
-int vb200_head_ce_loss(float* loss, const void* head_in_bf16, const void* W_bf16, const float* bias,
+int vb200_head_ce_loss(float* loss, const void* head_in, vb200_dtype head_in_dtype, const void* W,
+                       const float* bias,
                        const int32_t* targets, int32_t n_rows, int32_t d, int32_t n_levels, int32_t K,
                        vb200_stream_t stream);
 
 /* Scratch the caller provides for one denoiser forward over M packed rows, M_resp of them response
  * rows (the library never allocates; reference: the activations of Base.forward base.py:427-443).
  * sizes[7] receives the byte sizes, each rounded up to 256 B, in this order:
- *   x fp32 (M, d) | h bf16 (M, d) | qkv bf16 (M, 3d) | att bf16 (M, d) | ff bf16 (M, 4d) |
- *   head_in bf16 (M_resp, d) | logits logits_dtype (M_resp, n_out).
+ *   x fp32 (M, d) | h 16-bit (M, d) | qkv bf16 (M, 3d) | att bf16 (M, d) | ff 16-bit (M, 4d) |
+ *   head_in 16-bit (M_resp, d) | logits logits_dtype (M_resp, n_out).
  * Returns their sum, or a negative vb200_status. */
 int64_t vb200_workspace_bytes(int64_t M, int64_t M_resp, int32_t d, int32_t n_out,
                               vb200_dtype logits_dtype, int64_t* sizes);

@@ -407,13 +407,14 @@ def test_head_posterior_sample_fused_vs_separate_kernels(L):
         assert chi2 < dof + 6 * math.sqrt(2 * dof), (xt_val, chi2, dof)
 
 
+@pytest.mark.parametrize("act", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("rows,K,levels,d", [(77, 1024, 8, 128), (600, 512, 3, 64), (1000, 256, 1, 256)])
-def test_head_ce_loss_matches_torch(L, rows, K, levels, d):
+def test_head_ce_loss_matches_torch(L, rows, K, levels, d, act):
     """vb200_head_ce_loss (cross-entropy as the classifier GEMM's epilogue, no logits in memory)
-    against torch's cross-entropy on fp32 logits of the same bf16 operands."""
+    against torch's cross-entropy on fp32 logits of the same 16-bit operands (both bf16 or both fp16)."""
     g = torch.Generator().manual_seed(rows)
-    head_in = torch.randn(rows, d, generator=g).bfloat16().to(DEV)
-    W = (torch.randn(levels * K, d, generator=g) * 0.4).bfloat16().to(DEV)
+    head_in = torch.randn(rows, d, generator=g).to(act).to(DEV)
+    W = (torch.randn(levels * K, d, generator=g) * 0.4).bfloat16().to(act).to(DEV)
     bias = torch.randn(levels * K, generator=g).to(DEV)
     tgt = torch.randint(0, K, (rows, levels), generator=g, dtype=torch.int32).to(DEV)
     tgt[0, 0], tgt[-1, -1] = 0, K - 1                    # first / last class of a level
@@ -442,3 +443,57 @@ def test_q_sample_philox_uniform_transition_law(L):
     chi2 = (((others - exp_o) ** 2) / exp_o).sum().item()
     assert chi2 < (K - 2) + 6 * math.sqrt(2 * (K - 2)), chi2
     assert int(out.min()) >= 0 and int(out.max()) < K
+
+
+# ---------------------------------------------------------------- fp16 activations next to bf16 weights
+def test_fp16_activations(L):
+    """The GEMM operands may both be fp16 instead of bf16 (tcgen05 kind::f16 wants rows and weights in ONE
+    format), and the norm / gather kernels write fp16 rows for them.  Same references as the bf16 cases,
+    with fp16's tolerance; conversions saturate instead of producing inf; mixed formats are refused."""
+    from oracle import denoiser as on
+    # GEMM with an fp16 A operand, every tiling the launcher may pick, both kernels
+    for (M, N, K), epi, dt in (((1027, 3072, 1024), L.EPI_NONE, torch.bfloat16), ((1027, 1024, 4096), L.EPI_BIAS_RESIDUAL, torch.float32),
+                               ((4200, 4096, 1024), L.EPI_BIAS_GELU, torch.float16), ((257, 72, 200), L.EPI_BIAS, torch.float32)):
+        g = torch.Generator().manual_seed(M)
+        A = (torch.randn(M, K, generator=g)).to(torch.float16).to(DEV)
+        W = _rand_bf16((N, K), 2, K ** -0.5).to(torch.float16)
+        bias = torch.randn(N, generator=g).to(DEV)
+        resid = torch.randn(M, N, generator=g).to(DEV)
+        acc = A.float() @ W.float().t()
+        ref = {L.EPI_NONE: acc, L.EPI_BIAS: acc + bias, L.EPI_BIAS_GELU: torch.nn.functional.gelu(acc + bias),
+               L.EPI_BIAS_RESIDUAL: resid + acc + bias}[epi]
+        for simt in (False, True):
+            out = resid.clone() if epi == L.EPI_BIAS_RESIDUAL else torch.full((M, N), float("nan"), dtype=dt, device=DEV)
+            L.gemm_bf16(out, A, W, None if epi == L.EPI_NONE else bias, residual=out if epi == L.EPI_BIAS_RESIDUAL else None,
+                        epi=epi, simt=simt)
+            tol = {torch.float32: 2e-3, torch.bfloat16: 2e-2, torch.float16: 4e-3}[dt]
+            err = (out.float() - ref).abs().max().item()
+            assert err < tol * max(1.0, ref.abs().max().item()), ((M, N, K), simt, err)
+    # AdaLN / LayerNorm / gather with fp16 outputs: one fp16 ulp (2^-10 relative)
+    M, d, B = 333, 1024, 3
+    g = torch.Generator().manual_seed(6)
+    x = (torch.randn(M, d, generator=g) * 3 + 0.5)
+    emb = torch.randn(7, 2 * d, generator=g) * 0.1
+    row_utt = torch.sort(torch.randint(0, B, (M,), generator=g)).values.to(torch.int32)
+    lv = torch.tensor([3, 0, 6], dtype=torch.int32)
+    ref = on.adaln(x[:, None, :], emb, lv[row_utt.long()].long())[:, 0]
+    table = torch.cat([emb[:, :d].exp(), emb[:, d:]], dim=-1).to(DEV)
+    out = torch.empty(M, d, dtype=torch.float16, device=DEV)
+    L.adaln(out, x.to(DEV), table, lv.to(DEV), row_utt.to(DEV))
+    assert ((out.float().cpu() - ref).abs() <= ref.abs() * 2 ** -10 + 2e-4).all()
+    w, b = torch.randn(d, generator=g), torch.randn(d, generator=g)
+    ref = torch.nn.functional.layer_norm(x, (d,), w, b, 1e-5)
+    L.layernorm(out, x.to(DEV), w.to(DEV), b.to(DEV))
+    assert ((out.float().cpu() - ref).abs() <= ref.abs() * 2 ** -10 + 2e-4).all()
+    xs = x.clone()
+    xs[0, :4] = torch.tensor([1e6, -1e6, 65504.0, 70000.0])            # beyond fp16: saturate, never inf
+    idx = torch.tensor([5, 0, 332, 17], dtype=torch.int32)
+    o2 = torch.empty(4, d, dtype=torch.float16, device=DEV)
+    L.gather_rows_bf16(o2, xs.to(DEV), idx.to(DEV))
+    exp = xs[idx.long()].clamp(-65504, 65504).half()
+    assert torch.equal(o2.cpu(), exp) and torch.isfinite(o2).all()
+    with pytest.raises(L.VB200Error):
+        L.adaln(torch.empty(M, d, dtype=torch.float32, device=DEV), x.to(DEV), table, lv.to(DEV), row_utt.to(DEV))
+    with pytest.raises(AssertionError):          # fp16 rows against bf16 weights: the hardware faults on it
+        L.gemm_bf16(torch.empty(8, 16, device=DEV), torch.zeros(8, 16, dtype=torch.float16, device=DEV),
+                    torch.zeros(16, 16, dtype=torch.bfloat16, device=DEV))

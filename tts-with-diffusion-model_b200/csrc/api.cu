@@ -160,12 +160,17 @@ extern "C" int64_t vb200_workspace_bytes(int64_t M, int64_t M_resp, int32_t d, i
 }
 
 extern "C" int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_dtype logits_dtype,
-                                           const void* head_in_bf16, const void* W_bf16, const float* bias,
+                                           const void* head_in_bf16, vb200_dtype head_in_dtype,
+                                           const void* W_bf16, const float* bias,
                                            int32_t n_rows, int32_t d, int32_t n_levels, int32_t K,
                                            const int32_t* x_t, const int32_t* row_utt, const int32_t* t_utt,
                                            const int32_t* utt, const float* table, int32_t S,
                                            vb200_transition tr, vb200_noise noise, const float* uniforms,
                                            uint64_t seed, vb200_stream_t stream) {
+  if (head_in_dtype != VB200_BF16 && head_in_dtype != VB200_F16) {
+    vb200::set_error("head_posterior_sample: head_in must be bf16 or f16");
+    return VB200_ERR_INVALID;
+  }
   // fused form: the reverse step runs as the GEMM's epilogue and `logits` stays untouched
   static int fused = -1;
   if (fused < 0) {
@@ -179,9 +184,9 @@ extern "C" int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_d
     }
     return vb200::head_sample_fused(x_out, head_in_bf16, W_bf16, bias, x_t, row_utt, t_utt, utt, table, n_rows, d,
                              n_levels, K, S, static_cast<int>(tr), static_cast<int>(noise), seed,
-                             static_cast<cudaStream_t>(stream));
+                             head_in_dtype == VB200_F16, static_cast<cudaStream_t>(stream));
   }
-  const int rc = vb200_gemm_bf16(logits, logits_dtype, head_in_bf16, W_bf16, bias, nullptr, n_rows,
+  const int rc = vb200_gemm_bf16(logits, logits_dtype, head_in_bf16, head_in_dtype, W_bf16, bias, nullptr, n_rows,
                                  n_levels * K, d, VB200_EPI_BIAS, stream);
   if (rc != VB200_OK) return rc;
   return vb200_posterior_sample_from_logits(x_out, nullptr, logits, logits_dtype,
@@ -189,7 +194,8 @@ extern "C" int vb200_head_posterior_sample(int32_t* x_out, void* logits, vb200_d
                                             table, n_rows, n_levels, K, S, tr, noise, uniforms, seed, stream);
 }
 
-extern "C" int vb200_head_ce_loss(float* loss, const void* head_in_bf16, const void* W_bf16, const float* bias,
+extern "C" int vb200_head_ce_loss(float* loss, const void* head_in_bf16, vb200_dtype head_in_dtype,
+                                  const void* W_bf16, const float* bias,
                                   const int32_t* targets, int32_t n_rows, int32_t d, int32_t n_levels, int32_t K,
                                   vb200_stream_t stream) {
   if (n_rows == 0) return VB200_OK;
@@ -202,6 +208,10 @@ extern "C" int vb200_head_ce_loss(float* loss, const void* head_in_bf16, const v
                      n_rows, d, n_levels, K);
     return VB200_ERR_UNSUPPORTED;
   }
+  if (head_in_dtype != VB200_BF16 && head_in_dtype != VB200_F16) {
+    vb200::set_error("head_ce_loss: head_in must be bf16 or f16");
+    return VB200_ERR_INVALID;
+  }
   return vb200::head_ce_fused(loss, head_in_bf16, W_bf16, bias, targets, n_rows, d, n_levels, K,
-                              static_cast<cudaStream_t>(stream));
+                              head_in_dtype == VB200_F16, static_cast<cudaStream_t>(stream));
 }

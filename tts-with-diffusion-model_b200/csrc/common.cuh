@@ -35,9 +35,9 @@ bool head_sample_supported(int d, int K, int noise);
 int head_sample_fused(int32_t* x_out, const void* head_in, const void* W, const float* bias, const int32_t* x_t,
                       const int32_t* row_utt, const int32_t* t_utt, const int32_t* utt, const float* table,
                       int n_rows, int d, int n_levels, int K, int S, int tr, int noise, uint64_t seed,
-                      cudaStream_t st);
+                      int in_f16, cudaStream_t st);
 int head_ce_fused(float* loss_out, const void* head_in, const void* W, const float* bias, const int32_t* targets,
-                  int n_rows, int d, int n_levels, int K, cudaStream_t st);
+                  int n_rows, int d, int n_levels, int K, int in_f16, cudaStream_t st);
 
 // Programmatic dependent launch (PDL), opt-in with VB200_PDL=1.  Every kernel of the denoise step
 // goes through launch_pdl() and brackets its first access to memory that an earlier kernel
@@ -362,12 +362,15 @@ __device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, 
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
+// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.  A and B carry separate format
+// fields (0 = F16, 1 = BF16), but the hardware only takes them EQUAL: fp16 rows against bf16 weights
+// raises an illegal-instruction fault on B200 (measured).  Clearing kIdescBf16 makes both operands
+// fp16 — used where the activation range is safe (11 significand bits against 8), see DESIGN.md §4.
+constexpr uint32_t kIdescBf16 = (1u << 7) | (1u << 10);
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, bool a_mn_major,
                                                        bool b_mn_major) {
   return (1u << 4)                         // D format: F32
-         | (1u << 7)                       // A format: BF16
-         | (1u << 10)                      // B format: BF16
+         | kIdescBf16                      // A and B format: BF16
          | ((a_mn_major ? 1u : 0u) << 15)  // A major
          | ((b_mn_major ? 1u : 0u) << 16)  // B major
          | ((N >> 3) << 17)                // N >> 3
@@ -379,8 +382,13 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-  __half2 v = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t v;                              // saturating: an outlier becomes +-65504, never inf
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(hi), "f"(lo));
+  return v;
+}
+// 16-bit activations: fp16 or bf16 chosen at run time (warp-uniform flag)
+__device__ __forceinline__ uint32_t pack_act16x2(float lo, float hi, bool f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
 
 // Packed fp32 pairs (sm_100 FFMA2 / FADD2): one issue slot per two lanes' worth of fp32 work
@@ -450,7 +458,7 @@ __device__ __forceinline__ float warp_max(float v) {
 template <int NV>
 __device__ __forceinline__ void adaln_row_finish(const float (&v)[NV][8], const float (&g)[NV][8],
                                                  const float (&bt)[NV][8], __nv_bfloat16* orow, int lane,
-                                                 float eps, float k, float c) {
+                                                 float eps, float k, float c, bool f16 = false) {
   constexpr int d = NV * 256;
   float s = 0.f;
 #pragma unroll
@@ -474,8 +482,8 @@ __device__ __forceinline__ void adaln_row_finish(const float (&v)[NV][8], const 
       y[e] = fmaf(g[i][e], h, bt[i][e]);
     }
     uint4 o;
-    o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-    o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+    o.x = pack_act16x2(y[0], y[1], f16); o.y = pack_act16x2(y[2], y[3], f16);
+    o.z = pack_act16x2(y[4], y[5], f16); o.w = pack_act16x2(y[6], y[7], f16);
     *reinterpret_cast<uint4*>(orow + i * 256 + lane * 8) = o;
   }
 }

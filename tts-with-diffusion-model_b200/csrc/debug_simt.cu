@@ -22,7 +22,7 @@ __device__ __forceinline__ void store_out<__half>(__half* p, float v) { *p = __f
 template <typename OutT>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(
     OutT* __restrict__ out, const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
-    const float* __restrict__ bias, const float* residual, int M, int N, int K, int epi) {
+    const float* __restrict__ bias, const float* residual, int M, int N, int K, int epi, int a_f16) {
   __shared__ float sa[32][33], sw[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
@@ -30,8 +30,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(
   for (int k0 = 0; k0 < K; k0 += 32) {
     for (int i = ty; i < 32; i += 8) {
       const int k = k0 + tx;
-      sa[i][tx] = (m0 + i < M && k < K) ? __bfloat162float(A[static_cast<size_t>(m0 + i) * K + k]) : 0.f;
-      sw[i][tx] = (n0 + i < N && k < K) ? __bfloat162float(W[static_cast<size_t>(n0 + i) * K + k]) : 0.f;
+      sa[i][tx] = !(m0 + i < M && k < K) ? 0.f
+                  : a_f16 ? __half2float(reinterpret_cast<const __half*>(A)[static_cast<size_t>(m0 + i) * K + k])
+                          : __bfloat162float(A[static_cast<size_t>(m0 + i) * K + k]);
+      sw[i][tx] = !(n0 + i < N && k < K) ? 0.f
+                  : a_f16 ? __half2float(reinterpret_cast<const __half*>(W)[static_cast<size_t>(n0 + i) * K + k])
+                          : __bfloat162float(W[static_cast<size_t>(n0 + i) * K + k]);
     }
     __syncthreads();
 #pragma unroll
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(256) attn_simt_kernel(
 
 using namespace vb200;
 
-extern "C" int vb200_gemm_bf16_simt(void* out, vb200_dtype out_dtype, const void* A, const void* W,
+extern "C" int vb200_gemm_bf16_simt(void* out, vb200_dtype out_dtype, const void* A, vb200_dtype a_dtype, const void* W,
                                     const float* bias, const float* residual, int32_t M, int32_t N,
                                     int32_t K, vb200_epilogue epi, vb200_stream_t stream) {
   if (M <= 0 || N <= 0) return VB200_OK;
@@ -107,11 +111,11 @@ extern "C" int vb200_gemm_bf16_simt(void* out, vb200_dtype out_dtype, const void
   const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(A);
   const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(W);
   if (out_dtype == VB200_F32)
-    gemm_simt_kernel<float><<<grid, block, 0, st>>>(static_cast<float*>(out), a, w, bias, residual, M, N, K, epi);
+    gemm_simt_kernel<float><<<grid, block, 0, st>>>(static_cast<float*>(out), a, w, bias, residual, M, N, K, epi, a_dtype == VB200_F16);
   else if (out_dtype == VB200_BF16)
-    gemm_simt_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<__nv_bfloat16*>(out), a, w, bias, residual, M, N, K, epi);
+    gemm_simt_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<__nv_bfloat16*>(out), a, w, bias, residual, M, N, K, epi, a_dtype == VB200_F16);
   else
-    gemm_simt_kernel<__half><<<grid, block, 0, st>>>(static_cast<__half*>(out), a, w, bias, residual, M, N, K, epi);
+    gemm_simt_kernel<__half><<<grid, block, 0, st>>>(static_cast<__half*>(out), a, w, bias, residual, M, N, K, epi, a_dtype == VB200_F16);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

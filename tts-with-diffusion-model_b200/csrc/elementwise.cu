@@ -156,7 +156,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256) norm_kernel(
     __nv_bfloat16* __restrict__ out, const float* __restrict__ x, const float* __restrict__ p0,
     const float* __restrict__ p1, const int32_t* __restrict__ level_utt,
-    const int32_t* __restrict__ row_utt, int M, int d, float eps, float k, float c) {
+    const int32_t* __restrict__ row_utt, int M, int d, float eps, float k, float c, int out_f16) {
   pdl_launch_dependents();
   pdl_wait();                                   // everything below reads / writes activations
   constexpr int MAXV = 8;  // d <= 2048
@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(256) norm_kernel(
           y[e] = gg[e] * h + bb[e];
         }
         uint4 o;
-        o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-        o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+        o.x = pack_act16x2(y[0], y[1], out_f16); o.y = pack_act16x2(y[2], y[3], out_f16);
+        o.z = pack_act16x2(y[4], y[5], out_f16); o.w = pack_act16x2(y[6], y[7], out_f16);
         *reinterpret_cast<uint4*>(orow + col) = o;
       }
     }
@@ -233,7 +233,7 @@ template <int NV>
 __global__ void __launch_bounds__(256) adaln_rows_kernel(
     __nv_bfloat16* __restrict__ out, const float* __restrict__ x, const float* __restrict__ table,
     const int32_t* __restrict__ level_utt, const int32_t* __restrict__ row_utt, int M, int rows_per_warp,
-    float eps, float k, float c) {
+    float eps, float k, float c, int out_f16) {
   pdl_launch_dependents();
   pdl_wait();                                   // everything below reads / writes activations
   constexpr int d = NV * 256;
@@ -258,13 +258,13 @@ __global__ void __launch_bounds__(256) adaln_rows_kernel(
       adaln_load_params<NV>(table, lvl, lane, g, bt);
       cached = lvl;
     }
-    adaln_row_finish<NV>(v, g, bt, out + static_cast<size_t>(r) * d, lane, eps, k, c);
+    adaln_row_finish<NV>(v, g, bt, out + static_cast<size_t>(r) * d, lane, eps, k, c, out_f16 != 0);
   }
 }
 
 __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(
     __nv_bfloat16* __restrict__ out, const float* __restrict__ x,
-    const int32_t* __restrict__ row_index, int n_rows, int d) {
+    const int32_t* __restrict__ row_index, int n_rows, int d, int out_f16) {
   pdl_launch_dependents();
   pdl_wait();                                   // everything below reads / writes activations
   const int lane = threadIdx.x & 31;
@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(256) gather_rows_bf16_kernel(
       const float4 a = *reinterpret_cast<const float4*>(xr + c);
       const float4 b = *reinterpret_cast<const float4*>(xr + c + 4);
       uint4 o;
-      o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
-      o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+      o.x = pack_act16x2(a.x, a.y, out_f16); o.y = pack_act16x2(a.z, a.w, out_f16);
+      o.z = pack_act16x2(b.x, b.y, out_f16); o.w = pack_act16x2(b.z, b.w, out_f16);
       *reinterpret_cast<uint4*>(orow + c) = o;
     }
   }
@@ -349,9 +349,11 @@ extern "C" int vb200_embed_gather(float* x_out, const void* text_w, const void* 
   return VB200_OK;
 }
 
-extern "C" int vb200_adaln(void* out_bf16, const float* x, const float* table,
+extern "C" int vb200_adaln(void* out_bf16, vb200_dtype out_dtype, const float* x, const float* table,
                            const int32_t* level_utt, const int32_t* row_utt, int32_t M, int32_t d,
                            float eps, float k, float c, vb200_stream_t stream) {
+  VB_REQUIRE(out_dtype == VB200_BF16 || out_dtype == VB200_F16, "adaln: out_dtype must be bf16 or f16");
+  const int f16 = out_dtype == VB200_F16;
   if (M <= 0) return VB200_OK;
   VB_REQUIRE(out_bf16 && x && table && level_utt && row_utt, "adaln: null pointer");
   VB_REQUIRE(d > 0 && d % 8 == 0 && d <= 2048, "adaln: d=%d must be a multiple of 8, <= 2048", d);
@@ -366,41 +368,46 @@ extern "C" int vb200_adaln(void* out_bf16, const float* x, const float* table,
     const int warps = (M + rpw - 1) / rpw;
     const int grid = (warps + 7) / 8;
     switch (d / 256) {
-      case 1: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<1>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c)); break;
-      case 2: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<2>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c)); break;
-      case 3: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<3>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c)); break;
-      default: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<4>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c)); break;
+      case 1: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<1>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c, f16)); break;
+      case 2: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<2>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c, f16)); break;
+      case 3: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<3>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c, f16)); break;
+      default: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<4>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c, f16)); break;
     }
   } else {
     VB_CHECK_CUDA(launch_pdl(norm_kernel<0>, dim3(row_grid(M, 8)), dim3(256), 0, st, 1, o, x, table,
-                             static_cast<const float*>(nullptr), level_utt, row_utt, M, d, eps, k, c));
+                             static_cast<const float*>(nullptr), level_utt, row_utt, M, d, eps, k, c, f16));
   }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
 
-extern "C" int vb200_layernorm(void* out_bf16, const float* x, const float* weight,
+extern "C" int vb200_layernorm(void* out_bf16, vb200_dtype out_dtype, const float* x, const float* weight,
                                const float* bias, int32_t M, int32_t d, float eps,
                                vb200_stream_t stream) {
+  VB_REQUIRE(out_dtype == VB200_BF16 || out_dtype == VB200_F16, "layernorm: out_dtype must be bf16 or f16");
+  const int f16 = out_dtype == VB200_F16;
   if (M <= 0) return VB200_OK;
   VB_REQUIRE(out_bf16 && x && weight && bias, "layernorm: null pointer");
   VB_REQUIRE(d > 0 && d % 8 == 0 && d <= 2048, "layernorm: d=%d must be a multiple of 8, <= 2048", d);
   if (M <= 0) return VB200_OK;
   VB_CHECK_CUDA(launch_pdl(norm_kernel<1>, dim3(row_grid(M, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
       static_cast<__nv_bfloat16*>(out_bf16), x, weight, bias, static_cast<const int32_t*>(nullptr),
-      static_cast<const int32_t*>(nullptr), M, d, eps, 0.f, 0.f));
+      static_cast<const int32_t*>(nullptr), M, d, eps, 0.f, 0.f, f16));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
 
-extern "C" int vb200_gather_rows_bf16(void* out_bf16, const float* x, const int32_t* row_index,
-                                      int32_t n_rows, int32_t d, vb200_stream_t stream) {
+extern "C" int vb200_gather_rows_bf16(void* out_bf16, vb200_dtype out_dtype, const float* x,
+                                      const int32_t* row_index, int32_t n_rows, int32_t d,
+                                      vb200_stream_t stream) {
+  VB_REQUIRE(out_dtype == VB200_BF16 || out_dtype == VB200_F16, "gather_rows: out_dtype must be bf16 or f16");
+  const int f16 = out_dtype == VB200_F16;
   if (n_rows <= 0) return VB200_OK;
   VB_REQUIRE(out_bf16 && x && row_index, "gather_rows: null pointer");
   VB_REQUIRE(d > 0 && d % 8 == 0, "gather_rows: d=%d must be a multiple of 8", d);
   if (n_rows <= 0) return VB200_OK;
   VB_CHECK_CUDA(launch_pdl(gather_rows_bf16_kernel, dim3(row_grid(n_rows, 8)), dim3(256), 0,
-                           static_cast<cudaStream_t>(stream), 1, static_cast<__nv_bfloat16*>(out_bf16), x, row_index, n_rows, d));
+                           static_cast<cudaStream_t>(stream), 1, static_cast<__nv_bfloat16*>(out_bf16), x, row_index, n_rows, d, f16));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

@@ -78,7 +78,8 @@ __device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
 template <int EPI, typename OutT, int CTAS, int BN>
 __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-    const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N, int K) {
+    const __grid_constant__ CUtensorMap tm_out, const float* __restrict__ bias, int M, int N, int K,
+    uint32_t a_is_f16) {
   using namespace gemm;
   using C = Cfg<CTAS, BN>;
   constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES, B_ROWS = C::B_ROWS;
@@ -185,7 +186,8 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     if (cta_rank == 0) {
       // ------------------------------------------------------------ MMA issuer (leader CTA of a pair)
       const bool leader = elect_one();
-      constexpr uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN, false, false);
+      // A (activations) and B (weights) are both bf16 or both fp16 (run-time)
+      const uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN, false, false) & ~(a_is_f16 ? kIdescBf16 : 0u);
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
@@ -320,8 +322,9 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
 
 // ---------------------------------------------------------------- host side
 template <int EPI, typename OutT>
-static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, const float* bias, int M, int N,
-                       int K, cudaStream_t st) {
+static int launch_gemm(void* out, vb200_dtype dt, const void* A, vb200_dtype a_dt, const void* W, const float* bias,
+                       int M, int N, int K, cudaStream_t st) {
+  const uint32_t a_f16 = a_dt == VB200_F16 ? 1u : 0u;
   using namespace gemm;
   // Four tilings, picked by estimated cycles = waves x k-steps x cycles per MMA (tools/mma_bench.cu):
   //   CTA pair 256x256 (~135 cycles per k-step, half as many schedulable units, + ~5 000 cycles per
@@ -358,9 +361,9 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
   }
   const int bn = narrow64 ? 64 : (narrow ? 128 : BN);
   CUtensorMap ta, tb, tout;
-  int rc = cached_tmap(&ta, VB200_BF16, A, K, M, static_cast<uint64_t>(K) * 2, BK, BM);
+  int rc = cached_tmap(&ta, a_dt, A, K, M, static_cast<uint64_t>(K) * 2, BK, BM);
   if (rc != VB200_OK) return rc;
-  rc = cached_tmap(&tb, VB200_BF16, W, K, N, static_cast<uint64_t>(K) * 2, BK, bn / ctas);
+  rc = cached_tmap(&tb, a_dt, W, K, N, static_cast<uint64_t>(K) * 2, BK, bn / ctas);
   if (rc != VB200_OK) return rc;
   const int esz = sizeof(OutT);   // store box: 32 rows x 128 bytes
   rc = cached_tmap(&tout, dt, out, N, M, static_cast<uint64_t>(N) * esz, 128 / esz, 32);
@@ -372,32 +375,32 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, const void* W, 
     if constexpr (sizeof(OutT) == 4) {
       auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 64>;
       VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
-      VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K));
+      VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K, a_f16));
     }
   } else if (narrow) {
     auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 128>;
     VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
-    VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K));
+    VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K, a_f16));
   } else if (ctas == 1) {
     auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 256>;
     VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
-    VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K));
+    VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K, a_f16));
   } else {
     auto kern = gemm_tcgen05_kernel<EPI, OutT, 2, 256>;
     VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
-    VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 2, ta, tb, tout, bias, M, N, K));
+    VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 2, ta, tb, tout, bias, M, N, K, a_f16));
   }
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
 
 template <int EPI>
-static int launch_gemm_dtype(void* out, vb200_dtype dt, const void* A, const void* W, const float* bias, int M,
-                             int N, int K, cudaStream_t st) {
+static int launch_gemm_dtype(void* out, vb200_dtype dt, const void* A, vb200_dtype a_dt, const void* W,
+                             const float* bias, int M, int N, int K, cudaStream_t st) {
   switch (dt) {
-    case VB200_F32: return launch_gemm<EPI, float>(out, dt, A, W, bias, M, N, K, st);
-    case VB200_BF16: return launch_gemm<EPI, __nv_bfloat16>(out, dt, A, W, bias, M, N, K, st);
-    case VB200_F16: return launch_gemm<EPI, __half>(out, dt, A, W, bias, M, N, K, st);
+    case VB200_F32: return launch_gemm<EPI, float>(out, dt, A, a_dt, W, bias, M, N, K, st);
+    case VB200_BF16: return launch_gemm<EPI, __nv_bfloat16>(out, dt, A, a_dt, W, bias, M, N, K, st);
+    case VB200_F16: return launch_gemm<EPI, __half>(out, dt, A, a_dt, W, bias, M, N, K, st);
   }
   set_error("gemm: unknown out dtype %d", static_cast<int>(dt));
   return VB200_ERR_INVALID;
@@ -407,10 +410,11 @@ static int launch_gemm_dtype(void* out, vb200_dtype dt, const void* A, const voi
 
 using namespace vb200;
 
-extern "C" int vb200_gemm_bf16(void* out, vb200_dtype out_dtype, const void* A, const void* W,
+extern "C" int vb200_gemm_bf16(void* out, vb200_dtype out_dtype, const void* A, vb200_dtype a_dtype, const void* W,
                                const float* bias, const float* residual, int32_t M, int32_t N,
                                int32_t K, vb200_epilogue epi, vb200_stream_t stream) {
   VB_REQUIRE(M >= 0 && N > 0 && K > 0, "gemm: bad sizes M=%d N=%d K=%d", M, N, K);
+  VB_REQUIRE(a_dtype == VB200_BF16 || a_dtype == VB200_F16, "gemm: A and W must be bf16 or f16");
   if (M == 0) return VB200_OK;                    // nothing to do (empty tensors carry null pointers)
   VB_REQUIRE(out && A && W, "gemm: null pointer");
   VB_REQUIRE(K % 8 == 0, "gemm: K=%d must be a multiple of 8 (TMA row stride is 16-byte granular)", K);
@@ -421,15 +425,15 @@ extern "C" int vb200_gemm_bf16(void* out, vb200_dtype out_dtype, const void* A, 
              "gemm: BIAS_RESIDUAL needs residual and fp32 output");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   switch (epi) {
-    case VB200_EPI_NONE: return launch_gemm_dtype<VB200_EPI_NONE>(out, out_dtype, A, W, bias, M, N, K, st);
-    case VB200_EPI_BIAS: return launch_gemm_dtype<VB200_EPI_BIAS>(out, out_dtype, A, W, bias, M, N, K, st);
-    case VB200_EPI_BIAS_GELU: return launch_gemm_dtype<VB200_EPI_BIAS_GELU>(out, out_dtype, A, W, bias, M, N, K, st);
+    case VB200_EPI_NONE: return launch_gemm_dtype<VB200_EPI_NONE>(out, out_dtype, A, a_dtype, W, bias, M, N, K, st);
+    case VB200_EPI_BIAS: return launch_gemm_dtype<VB200_EPI_BIAS>(out, out_dtype, A, a_dtype, W, bias, M, N, K, st);
+    case VB200_EPI_BIAS_GELU: return launch_gemm_dtype<VB200_EPI_BIAS_GELU>(out, out_dtype, A, a_dtype, W, bias, M, N, K, st);
     case VB200_EPI_BIAS_RESIDUAL:
       // out (+)= acc + bias is a TMA reduce-add into `out`; a distinct residual is copied in first
       if (residual != static_cast<const float*>(out))
         VB_CHECK_CUDA(cudaMemcpyAsync(out, residual, static_cast<size_t>(M) * N * sizeof(float),
                                       cudaMemcpyDeviceToDevice, st));
-      return launch_gemm<VB200_EPI_BIAS_RESIDUAL, float>(out, out_dtype, A, W, bias, M, N, K, st);
+      return launch_gemm<VB200_EPI_BIAS_RESIDUAL, float>(out, out_dtype, A, a_dtype, W, bias, M, N, K, st);
   }
   set_error("gemm: unknown epilogue %d", static_cast<int>(epi));
   return VB200_ERR_INVALID;

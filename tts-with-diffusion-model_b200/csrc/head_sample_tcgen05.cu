@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(hs::THREADS, 1) head_sample_kernel(
     const int32_t* __restrict__ x_t_all,
     const int32_t* __restrict__ row_utt, const int32_t* __restrict__ t_utt, const int32_t* __restrict__ utt,
     const float* __restrict__ table, int n_rows, int n_levels, int K, int Kd, int S, int transition,
-    uint32_t seed_lo, uint32_t seed_hi) {
+    uint32_t seed_lo, uint32_t seed_hi, uint32_t a_is_f16) {
   using namespace hs;
   const uint32_t cta_rank = cluster_ctarank();          // 0 = leader of the pair
   extern __shared__ uint8_t smem_raw[];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(hs::THREADS, 1) head_sample_kernel(
     if (cta_rank == 0) {
       // ------------------------------------------------------------ MMA issuer (leader CTA of the pair)
       const bool leader = elect_one();
-      constexpr uint32_t idesc = umma_idesc_bf16(BM * 2, BN, false, false);
+      const uint32_t idesc = umma_idesc_bf16(BM * 2, BN, false, false) & ~(a_is_f16 ? kIdescBf16 : 0u);   // rows and weights: both bf16 or both fp16
       int stage = 0; uint32_t phase = 0;
       int it = 0;
       for (int item = item0; item < num_items; item += item_stride) {
@@ -380,12 +380,12 @@ template <int NOISE>
 static int launch_head_sample(int32_t* x_out, float* loss_out, const void* head_in, const void* W, const float* bias,
                               const int32_t* x_t, const int32_t* row_utt, const int32_t* t_utt,
                               const int32_t* utt, const float* table, int n_rows, int d, int n_levels,
-                              int K, int S, int tr, uint64_t seed, cudaStream_t st) {
+                              int K, int S, int tr, uint64_t seed, int in_f16, cudaStream_t st) {
   using namespace hs;
   CUtensorMap ta, tb;
-  int rc = cached_tmap(&ta, VB200_BF16, head_in, d, n_rows, static_cast<uint64_t>(d) * 2, BK, BM);
+  int rc = cached_tmap(&ta, in_f16 ? VB200_F16 : VB200_BF16, head_in, d, n_rows, static_cast<uint64_t>(d) * 2, BK, BM);
   if (rc != VB200_OK) return rc;
-  rc = cached_tmap(&tb, VB200_BF16, W, d, static_cast<uint64_t>(n_levels) * K, static_cast<uint64_t>(d) * 2, BK, B_ROWS);
+  rc = cached_tmap(&tb, in_f16 ? VB200_F16 : VB200_BF16, W, d, static_cast<uint64_t>(n_levels) * K, static_cast<uint64_t>(d) * 2, BK, B_ROWS);
   if (rc != VB200_OK) return rc;
   const int items = ((n_rows + 2 * BM - 1) / (2 * BM)) * n_levels;
   const int groups = num_sms() / 2;
@@ -394,7 +394,7 @@ static int launch_head_sample(int32_t* x_out, float* loss_out, const void* head_
   VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
   VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 2, ta, tb, x_out, loss_out, bias, x_t, row_utt,
                            t_utt, utt, table, n_rows, n_levels, K, d, S, tr, static_cast<uint32_t>(seed),
-                           static_cast<uint32_t>(seed >> 32)));
+                           static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(in_f16 ? 1 : 0)));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }
@@ -407,20 +407,20 @@ bool head_sample_supported(int d, int K, int noise) {
 int head_sample_fused(int32_t* x_out, const void* head_in, const void* W, const float* bias,
                       const int32_t* x_t, const int32_t* row_utt, const int32_t* t_utt, const int32_t* utt,
                       const float* table, int n_rows, int d, int n_levels, int K, int S, int tr, int noise,
-                      uint64_t seed, cudaStream_t st) {
+                      uint64_t seed, int in_f16, cudaStream_t st) {
   if (noise == VB200_NOISE_GREEDY)
     return launch_head_sample<VB200_NOISE_GREEDY>(x_out, nullptr, head_in, W, bias, x_t, row_utt, t_utt, utt, table, n_rows,
-                                                  d, n_levels, K, S, tr, seed, st);
+                                                  d, n_levels, K, S, tr, seed, in_f16, st);
   return launch_head_sample<VB200_NOISE_PHILOX>(x_out, nullptr, head_in, W, bias, x_t, row_utt, t_utt, utt, table, n_rows, d,
-                                                n_levels, K, S, tr, seed, st);
+                                                n_levels, K, S, tr, seed, in_f16, st);
 }
 
 
 // classifier GEMM with per-token cross-entropy as its epilogue: loss[r, l] = -log softmax(logits[r, l, :])[target[r, l]]
 int head_ce_fused(float* loss_out, const void* head_in, const void* W, const float* bias, const int32_t* targets,
-                  int n_rows, int d, int n_levels, int K, cudaStream_t st) {
+                  int n_rows, int d, int n_levels, int K, int in_f16, cudaStream_t st) {
   return launch_head_sample<hs::MODE_CE>(nullptr, loss_out, head_in, W, bias, targets, nullptr, nullptr, nullptr,
-                                         nullptr, n_rows, d, n_levels, K, 1, VB200_UNIFORM, 0, st);
+                                         nullptr, n_rows, d, n_levels, K, 1, VB200_UNIFORM, 0, in_f16, st);
 }
 
 }  // namespace vb200

@@ -33,11 +33,11 @@ PROTOTYPES = {
     "vb200_version": ([], C.c_int),
     "vb200_device_sms": ([], C.c_int),
     "vb200_embed_gather": ([_p] * 13 + [_i32] * 4 + [_p], C.c_int),
-    "vb200_adaln": ([_p] * 5 + [_i32, _i32, _f, _f, _f, _p], C.c_int),
-    "vb200_layernorm": ([_p] * 4 + [_i32, _i32, _f, _p], C.c_int),
-    "vb200_gather_rows_bf16": ([_p] * 3 + [_i32, _i32, _p], C.c_int),
-    "vb200_gemm_bf16": ([_p, C.c_int, _p, _p, _p, _p, _i32, _i32, _i32, C.c_int, _p], C.c_int),
-    "vb200_gemm_bf16_simt": ([_p, C.c_int, _p, _p, _p, _p, _i32, _i32, _i32, C.c_int, _p], C.c_int),
+    "vb200_adaln": ([_p, C.c_int] + [_p] * 4 + [_i32, _i32, _f, _f, _f, _p], C.c_int),
+    "vb200_layernorm": ([_p, C.c_int] + [_p] * 3 + [_i32, _i32, _f, _p], C.c_int),
+    "vb200_gather_rows_bf16": ([_p, C.c_int, _p, _p, _i32, _i32, _p], C.c_int),
+    "vb200_gemm_bf16": ([_p, C.c_int, _p, C.c_int, _p, _p, _p, _i32, _i32, _i32, C.c_int, _p], C.c_int),
+    "vb200_gemm_bf16_simt": ([_p, C.c_int, _p, C.c_int, _p, _p, _p, _i32, _i32, _i32, C.c_int, _p], C.c_int),
     "vb200_flash_attn_varlen": ([_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p], C.c_int),
     "vb200_attn_varlen_simt": ([_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p], C.c_int),
     "vb200_q_sample": ([_p] * 6 + [_i32, _i32, _i32, C.c_int, _p], C.c_int),
@@ -45,10 +45,11 @@ PROTOTYPES = {
         [_p, _p, _p, C.c_int, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, C.c_int, C.c_int, _p, _u64, _p],
         C.c_int),
     "vb200_head_posterior_sample": (
-        [_p, _p, C.c_int, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, C.c_int, C.c_int, _p, _u64, _p],
+        [_p, _p, C.c_int, _p, C.c_int, _p, _p, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _p, _i32, C.c_int, C.c_int, _p, _u64,
+         _p],
         C.c_int),
     "vb200_q_sample_philox": ([_p] * 5 + [_i32, _i32, _i32, C.c_int, _u64, _p], C.c_int),
-    "vb200_head_ce_loss": ([_p] * 5 + [_i32, _i32, _i32, _i32, _p], C.c_int),
+    "vb200_head_ce_loss": ([_p, _p, C.c_int, _p, _p, _p, _i32, _i32, _i32, _i32, _p], C.c_int),
     "vb200_workspace_bytes": ([_i64, _i64, _i32, _i32, C.c_int, C.POINTER(C.c_int64)], C.c_int64),
     "vb200_step_timesteps": ([_p, _i32, _i32, _p], C.c_int),
     "vb200_codes_to_bqt": ([_p, _p, _p, _i32, _i32, _i32, _i64, _p], C.c_int),
@@ -106,6 +107,13 @@ def dtype_code(dt: torch.dtype) -> int:
     return _DTYPES[dt]
 
 
+def act_code(t: torch.Tensor) -> int:
+    """dtype code of a 16-bit activation tensor (bf16 or fp16)."""
+    if t.dtype not in (torch.bfloat16, torch.float16):
+        raise VB200Error(f"16-bit activations must be bf16 or fp16, got {t.dtype}")
+    return _DTYPES[t.dtype]
+
+
 # ------------------------------------------------------------------ thin typed wrappers
 def embed_gather(x_out, text_w, prom_w, resp_w, sep, time_w, pe, text_ids, prom_ids, resp_ids, utt,
                  row_utt, t_utt, K, resp_levels_in):
@@ -118,19 +126,19 @@ def embed_gather(x_out, text_w, prom_w, resp_w, sep, time_w, pe, text_ids, prom_
 
 def adaln(out, x, table, level_utt, row_utt, eps=1e-5, k=0.1, c=2.0):
     M, d = x.shape
-    _check(load().vb200_adaln(ptr(out), ptr(x), ptr(table), ptr(level_utt), ptr(row_utt), M, d, eps, k, c,
-                              stream()), "vb200_adaln")
+    _check(load().vb200_adaln(ptr(out), act_code(out), ptr(x), ptr(table), ptr(level_utt), ptr(row_utt), M, d, eps,
+                              k, c, stream()), "vb200_adaln")
 
 
 def layernorm(out, x, weight, bias, eps=1e-5):
     M, d = x.shape
-    _check(load().vb200_layernorm(ptr(out), ptr(x), ptr(weight), ptr(bias), M, d, eps, stream()),
+    _check(load().vb200_layernorm(ptr(out), act_code(out), ptr(x), ptr(weight), ptr(bias), M, d, eps, stream()),
            "vb200_layernorm")
 
 
 def gather_rows_bf16(out, x, row_index):
     n, d = out.shape
-    _check(load().vb200_gather_rows_bf16(ptr(out), ptr(x), ptr(row_index), n, d, stream()),
+    _check(load().vb200_gather_rows_bf16(ptr(out), act_code(out), ptr(x), ptr(row_index), n, d, stream()),
            "vb200_gather_rows_bf16")
 
 
@@ -146,9 +154,9 @@ def gemm_bf16(out, A, W, bias=None, residual=None, epi=EPI_NONE, simt=False):
     M, K = A.shape
     N = W.shape[0]
     assert W.shape[1] == K and tuple(out.shape) == (M, N), (A.shape, W.shape, out.shape)
-    assert A.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+    assert A.dtype in (torch.bfloat16, torch.float16) and W.dtype == A.dtype, (A.dtype, W.dtype)
     fn = load().vb200_gemm_bf16_simt if simt else load().vb200_gemm_bf16
-    _check(fn(ptr(out), dtype_code(out.dtype), ptr(A), ptr(W), ptr(bias), ptr(residual), M, N, K, epi,
+    _check(fn(ptr(out), dtype_code(out.dtype), ptr(A), act_code(A), ptr(W), ptr(bias), ptr(residual), M, N, K, epi,
               stream()), "vb200_gemm_bf16")
 
 
@@ -181,7 +189,7 @@ def head_posterior_sample(x_out, logits, head_in, W, bias, x_t, row_utt, t_utt, 
     n_rows, d = head_in.shape
     _check(load().vb200_head_posterior_sample(
         ptr(x_out), ptr(logits), dtype_code(logits.dtype) if logits is not None else dtype_code(torch.float16),
-        ptr(head_in), ptr(W), ptr(bias), n_rows, d,
+        ptr(head_in), act_code(head_in), ptr(W), ptr(bias), n_rows, d,
         n_levels, K, ptr(x_t), ptr(row_utt), ptr(t_utt), ptr(utt), ptr(table), table.shape[0], transition,
         noise, ptr(uniforms), seed, stream()), "vb200_head_posterior_sample")
 
@@ -195,8 +203,8 @@ def q_sample_philox(x_out, x0, t_tok, mask, table, K, transition, seed=0):
 def head_ce_loss(loss, head_in, W, bias, targets, n_levels, K):
     """loss[r, l] = -log softmax(head_in[r] W_l^T + b_l)[targets[r, l]] as the classifier GEMM's epilogue."""
     n_rows, d = head_in.shape
-    _check(load().vb200_head_ce_loss(ptr(loss), ptr(head_in), ptr(W), ptr(bias), ptr(targets), n_rows, d,
-                                     n_levels, K, stream()), "vb200_head_ce_loss")
+    _check(load().vb200_head_ce_loss(ptr(loss), ptr(head_in), act_code(head_in), ptr(W), ptr(bias), ptr(targets),
+                                     n_rows, d, n_levels, K, stream()), "vb200_head_ce_loss")
 
 
 def head_fused(d, K, noise) -> bool:
