@@ -160,8 +160,8 @@ def config_dict(wl, n_gpus):
                         f"{transition}; sharded by utterance over {n_gpus} GPU(s)",
             "global_batch": B, "frames": t_resp, "denoise_steps": timesteps - 1, "transition": transition,
             "l2_policy": "per-step working set (activations > 1 GB per GPU at every N) exceeds the 126 MB L2; no flush needed",
-            "operands": "16-bit tensor-core operands, fp32 accumulate: fp16 for the normalised rows, the FFN hidden, the "
-                        "classifier input and their weights; bf16 for qkv, attention and to_out; fp32 residual stream",
+            "operands": "16-bit tensor-core operands, fp32 accumulate: bf16 everywhere except the classifier GEMM "
+                        "(fp16 rows and weights); fp32 residual stream",
             "parallelism": f"utterance-sharded x{n_gpus}, one final all-gather"}
 
 
@@ -387,7 +387,7 @@ def run_ours(args, wl):
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "bf16/fp16", "data": "synthetic", "config": config_dict(wl, world),
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config_dict(wl, world),
                 "denoise_step_ms": step_total_ms, "wall_s_timed_region": t_wall,
                 "clocks": clocks.summary(),
                 "e2e": {"value": tokens_per_step / (e2e / 1e3), "unit": UNIT, "ms_per_step": e2e,

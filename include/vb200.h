@@ -89,10 +89,11 @@ int vb200_embed_gather(float* x_out, const void* text_w, const void* prom_w, con
 
 /* 16-bit operands.  The two operands of a GEMM are both bf16 or both fp16 (`*_dtype` = VB200_BF16 |
  * VB200_F16 names the dtype of the rows AND of the weights: tcgen05 kind::f16 faults on mixed formats).
- * The engine keeps the normalised rows, the FFN hidden and the classifier input — and the weights they
- * meet — in fp16 (11 significand bits against 8; conversions saturate at +-65504): with bf16 there the
- * logits of the full model are 2.2e-2 off the fp32 reference, with fp16 5.5e-3; qkv, the
- * attention output and the to_out weights stay bf16, and so do the embedding tables. */
+ * fp16 has 11 significand bits against 8 and is safe for the normalised rows, the FFN hidden and the
+ * classifier input (conversions saturate at +-65504) but costs power; the engine uses it for the
+ * classifier input by default, which brings the full model's logits from 2.2e-2 to 1.4e-2 off the fp32
+ * reference (DESIGN.md §2 has the table).  qkv, the attention output, the to_out weights and the
+ * embedding tables are always bf16. */
 
 /* N1: AdaLN.forward (base.py:145-158): h = LN(x) (no affine, eps); h = c(1-k h)h;
  * y = gamma_l * h + beta_l with table (n_rows, 2d) fp32 = [exp(log gamma) | beta] (exp applied

@@ -30,12 +30,23 @@ def sinusoidal_table(n: int, d_model: int) -> torch.Tensor:
     return torch.cat([ang.sin(), ang.cos()], dim=-1).contiguous()
 
 
-# 16-bit format of the GEMM operands whose range is safe in fp16 — the normalised rows, the FFN hidden, the
-# classifier input, and the weights they meet (tcgen05 takes both operands in ONE format): 11 significand
-# bits against bf16's 8 bring the full model's logits from 2.2e-2 to 5.5e-3 off the fp32 reference
-# (DESIGN.md §4).  qkv, the attention output and the to_out weights stay bf16.  VB200_ACT=bf16 switches
-# everything back to bf16 (A/B measurements).
-ACT_DTYPE = torch.bfloat16 if os.environ.get("VB200_ACT", "f16") == "bf16" else torch.float16
+# 16-bit format of the GEMM operands whose range is safe in fp16 — the normalised rows (h), the FFN hidden (ff),
+# the classifier input (head), each with the weights it meets (tcgen05 takes both operands in ONE format): 11
+# significand bits against bf16's 8.  Measured on the full model, logits max-abs error against the
+# fp32 reference / reverse-loop time on one box:  none 2.2e-2 (over the 2e-2 bar) / 1302 ms;  head 1.4e-2 / 1306;
+# head,ff 1.2e-2 / 1319;  head,h 1.1e-2 / 1331;  all 7.6e-3 / 1343 — fp16 MMAs cost power, and the step is
+# power-capped, so each GEMM moved to fp16 is paid for in clocks.  Default: the classifier input alone (the
+# largest single error source, 3 % of the FLOPs).  VB200_ACT picks another set: "f16" = all three, "bf16" = none,
+# or a comma list such as "head,ff".  qkv, the attention output and the to_out weights are always bf16.
+def _act_dtypes():
+    v = os.environ.get("VB200_ACT", "head")
+    on = {"h", "ff", "head"} if v == "f16" else (set() if v == "bf16" else {x.strip() for x in v.split(",")})
+    if not on <= {"h", "ff", "head"}:
+        raise ValueError(f"VB200_ACT={v!r}: expected f16, bf16 or a comma list of h, ff, head")
+    return {k: (torch.float16 if k in on else torch.bfloat16) for k in ("h", "ff", "head")}
+
+
+ACT = _act_dtypes()
 
 
 class PackedWeights:
@@ -46,7 +57,7 @@ class PackedWeights:
         if dev.type != "cuda":
             raise L.VB200Error("PackedWeights needs a CUDA device (no CPU fallback)")
         bf = lambda t: t.detach().to(dev, torch.bfloat16).contiguous()
-        a16 = lambda t: t.detach().to(dev, ACT_DTYPE).contiguous()      # weights that meet fp16 activations
+        as_ = lambda t, k: t.detach().to(dev, ACT[k]).contiguous()      # weights in the format of the rows they meet
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
         self.device = dev
         self.n_heads, self.n_layers, self.norm_type = n_heads, n_layers, norm_type
@@ -66,11 +77,11 @@ class PackedWeights:
         for i in range(n_layers):
             p = f"blocks.{i}"
             ly = dict(
-                w_qkv=a16(sd[f"{p}.attn.block.to_qkv.weight"]),
+                w_qkv=as_(sd[f"{p}.attn.block.to_qkv.weight"], "h"),
                 w_out=bf(sd[f"{p}.attn.block.to_out.weight"]),
                 b_out=f32(sd[f"{p}.attn.block.to_out.bias"]),
-                w_ff1=a16(sd[f"{p}.ffn.block.0.weight"]), b_ff1=f32(sd[f"{p}.ffn.block.0.bias"]),
-                w_ff2=a16(sd[f"{p}.ffn.block.3.weight"]), b_ff2=f32(sd[f"{p}.ffn.block.3.bias"]),
+                w_ff1=as_(sd[f"{p}.ffn.block.0.weight"], "h"), b_ff1=f32(sd[f"{p}.ffn.block.0.bias"]),
+                w_ff2=as_(sd[f"{p}.ffn.block.3.weight"], "ff"), b_ff2=f32(sd[f"{p}.ffn.block.3.bias"]),
             )
             for which in ("attn", "ffn"):
                 if norm_type == "adaln":
@@ -80,7 +91,7 @@ class PackedWeights:
                 else:
                     ly[f"norm_{which}"] = (f32(sd[f"{p}.{which}.norm.weight"]), f32(sd[f"{p}.{which}.norm.bias"]))
             self.layers.append(ly)
-        self.w_cls = a16(sd["classifier.weight"])
+        self.w_cls = as_(sd["classifier.weight"], "head")
         self.b_cls = f32(sd["classifier.bias"])
         self.n_out = int(self.w_cls.shape[0])
         self._pe = None
@@ -182,10 +193,9 @@ class DenoiserEngine:
         ldt = logits_dtype or self.logits_dtype
         total, sizes = L.workspace_bytes(M, Mr, d, w.n_out, ldt)
         flat = e(max(total, 1), dt=torch.uint8)
-        a16 = ACT_DTYPE      # normalised rows, FFN hidden, classifier input (see ACT_DTYPE above)
-        shapes = {"x": ((M, d), torch.float32), "h": ((M, d), a16), "qkv": ((M, 3 * d), torch.bfloat16),
-                  "att": ((M, d), torch.bfloat16), "ff": ((M, 4 * d), a16),
-                  "head_in": ((Mr, d), a16), "logits": ((Mr, w.n_out), ldt)}
+        shapes = {"x": ((M, d), torch.float32), "h": ((M, d), ACT["h"]), "qkv": ((M, 3 * d), torch.bfloat16),
+                  "att": ((M, d), torch.bfloat16), "ff": ((M, 4 * d), ACT["ff"]),
+                  "head_in": ((Mr, d), ACT["head"]), "logits": ((Mr, w.n_out), ldt)}
         views, off = {}, 0
         for name, size in zip(L.WS_FIELDS, sizes):
             shape, dt = shapes[name]
