@@ -479,3 +479,40 @@ def test_full_size_logits_vs_oracle():
         top2 = r.topk(2, dim=-1).values
         clear = (top2[..., 0] - top2[..., 1]) > 4e-2
         assert torch.equal(g_.cpu().argmax(-1)[clear], r.argmax(-1)[clear])
+
+
+def test_c1_config_reverse_loop_vs_oracle():
+    """BASELINE.json configs[0] / SURVEY C1, literally: the quarter model (d = 256, 4 heads, 12 layers,
+    K = 1024 x 8 levels), one utterance of 3 s (30 phones + 225 prompt frames + 225 frames, T = 482), 50
+    denoise steps, uniform transition, the reference's noise convention (supplied uniforms).  Every seventh
+    step of the CUDA trajectory is re-done by the oracle (fp32 denoiser -> fp16 logits -> dense fp16-table
+    p_sample with the same uniforms): tokens must agree wherever the oracle's noisy top-2 margin is clear."""
+    import detrand
+    from oracle import denoiser as on
+    from oracle.d3pm import D3PM
+    K, d, h, nl, S = 1024, 256, 4, 12, 51
+    m, sd = _make(K, d, h, nl, S, "uniform", seed=5)
+    text, proms, _ = _batch(K, [(30, 225, 225)], 21)
+    x_T = torch.from_numpy(detrand.integers(77, 0, K, (225, 8)))
+    noise = {t: torch.from_numpy(detrand.uniform(1000 + t, (225 * 8, K))) for t in range(1, S)}
+    trace = []
+    out = m.generate_audio([text[0].to(DEV)], [proms[0].to(DEV)], [x_T.to(DEV)],
+                           uniforms_fn=lambda t: noise[t].to(DEV), trace=trace, use_graph=False)
+    assert out[0].shape == (225, 8) and len(trace) == S - 1
+    assert int(out[0].min()) >= 0 and int(out[0].max()) < K
+    orc = D3PM(S, K, "uniform")
+    steps = list(range(S - 1, 0, -1))
+    checked = agree = 0
+    for i in range(0, len(steps), 7):
+        t = steps[i]
+        prev = x_T if i == 0 else trace[i - 1].cpu().long()
+        lg = on.diffusion_logits(sd, text, proms, [prev], torch.tensor([t]), h, nl)[0].to(torch.float16)   # (225, 8, K)
+        u = noise[t].view(225, 8, K)
+        ref, post = orc.p_sample(lg, torch.full((225,), t), prev.to(torch.int32), u)
+        g = -torch.log(-torch.log(u.clamp(min=torch.finfo(torch.float32).tiny)))
+        top2 = (post.float() + g).topk(2, dim=-1).values
+        clear = (top2[..., 0] - top2[..., 1]) > 0.08
+        got = trace[i].cpu().long()
+        checked += int(clear.sum())
+        agree += int((got[clear] == ref[clear]).sum())
+    assert checked > 0.8 * 8 * 225 * 8 and agree == checked, (agree, checked)
