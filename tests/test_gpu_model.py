@@ -479,6 +479,14 @@ def test_full_size_logits_vs_oracle():
         top2 = r.topk(2, dim=-1).values
         clear = (top2[..., 0] - top2[..., 1]) > 4e-2
         assert torch.equal(g_.cpu().argmax(-1)[clear], r.argmax(-1)[clear])
+    # the long-form sequence of BASELINE configs[3] (C4: 2 250 frames, T = 2 527) on its own
+    text, proms, xt = _batch(K, [(50, 225, 2250)], 19)
+    t = torch.tensor([21])
+    ref = on.diffusion_logits(sd, text, proms, xt, t, h, nl)[0]
+    got = m.denoise_logits([x.to(DEV) for x in text], [x.to(DEV) for x in proms], [x.to(DEV) for x in xt], t)[0].cpu()
+    err = (got - ref).abs().max().item()
+    print(f"full-size logits vs oracle, C4 sequence: max-abs {err:.4f}, rms {(got - ref).pow(2).mean().sqrt().item():.5f}")
+    assert err <= 2e-2, err
 
 
 def test_c1_config_reverse_loop_vs_oracle():
