@@ -272,3 +272,17 @@ def test_ar_discrete_compat_matches_reference_module(golden_dir):
     assert (m.num_classes, m.mask_id, m.timesteps, m.transition) == (1025, 512, 100, "absorbing")
     with pytest.raises(ValueError):
         m.generate_audio([text, text], [proms, proms])
+
+
+def test_operand_format_selection(monkeypatch):
+    """VB200_ACT picks which GEMM operand sets are fp16 (engine._act_dtypes): default = classifier only."""
+    from vall_e.b200 import engine
+    monkeypatch.delenv("VB200_ACT", raising=False)
+    assert engine._act_dtypes() == {"h": torch.bfloat16, "ff": torch.bfloat16, "head": torch.float16}
+    for v, want in (("bf16", set()), ("f16", {"h", "ff", "head"}), ("head,ff", {"head", "ff"}), ("h", {"h"})):
+        monkeypatch.setenv("VB200_ACT", v)
+        got = engine._act_dtypes()
+        assert {k for k, dt in got.items() if dt == torch.float16} == want, v
+    monkeypatch.setenv("VB200_ACT", "fp8")
+    with pytest.raises(ValueError):
+        engine._act_dtypes()
