@@ -11,13 +11,17 @@ weights.  The 256 utterances are sharded by utterance over the N ranks (strong s
 work fixed), no collective inside the loop, one all-gather of the codes at the end.
 
 One "step" = one full pass of the hot path over one batch: all 50 denoise steps for every
-utterance of the batch -> B * 750 * 8 codec tokens.  `value` = tokens / s with inputs resident
-in HBM; `e2e` = the same through Diffusion.generate_audio() from pinned host tensors with the
-codes read back to the host.  One JSON line on stdout (rank 0).
+utterance of the batch -> B * 750 * 8 codec tokens.  Both timed arms go through the product's own
+multi-GPU entry point, ``vall_e.b200.shard.generate_sharded`` around ``Diffusion.generate_audio``:
+`value` with the batch already resident in HBM, `e2e` from pinned host tensors with the gathered
+codes read back to the host.  Every utterance is synthesised from its GLOBAL id, and the Philox
+noise is keyed by it, so the generated codes — `codes_sha256` — do not depend on N.
+One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -28,7 +32,8 @@ import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
-for p in (str(ROOT), str(ROOT / "tts-with-diffusion-model_b200")):
+PKG = ROOT / "tts-with-diffusion-model_b200"
+for p in (str(ROOT), str(PKG)):
     if p not in sys.path:
         sys.path.insert(0, p)
 
@@ -36,20 +41,22 @@ import torch  # noqa: E402
 
 WORKLOADS = {
     #        B    T_txt T_prom T_resp timesteps transition
+    "c1": (1, 30, 225, 225, 51, "uniform"),       # BASELINE configs[0]: the CPU-runnable case (quarter model)
     "c2": (1, 50, 225, 750, 51, "absorbing"),
     "c3": (256, 50, 225, 750, 51, "absorbing"),
     "c4": (16, 50, 225, 2250, 51, "absorbing"),
     "c5": (64, 50, 225, 300, 26, "uniform"),      # BASELINE configs[4], one point of its sweep: S = 25, uniform
 }
 MODEL = dict(n_tokens=1024, d_model=1024, n_heads=16, n_layers=12)
+QUARTER = dict(n_tokens=1024, d_model=256, n_heads=4, n_layers=12)
 METRIC, UNIT = "codec_tokens_per_sec", "tokens/s"
 
 
-def synth_batch(n, t_txt, t_prom, seed):
-    g = torch.Generator().manual_seed(seed)
-    text = [torch.randint(1, MODEL["n_tokens"], (t_txt,), generator=g) for _ in range(n)]
-    proms = [torch.randint(0, MODEL["n_tokens"], (t_prom, 8), generator=g) for _ in range(n)]
-    return text, proms
+def synth_utterance(gid: int, t_txt: int, t_prom: int):
+    """(text, prompt) of the utterance with GLOBAL id `gid` — independent of rank, batch and N."""
+    g = torch.Generator().manual_seed(0x5EED0000 + gid)
+    return (torch.randint(1, MODEL["n_tokens"], (t_txt,), generator=g),
+            torch.randint(0, MODEL["n_tokens"], (t_prom, 8), generator=g))
 
 
 def measured_peaks():
@@ -58,6 +65,14 @@ def measured_peaks():
         d = json.loads(f.read_text())
         return d.get("bf16_tflops_sustained", 1378.2), d.get("hbm_gbs", 6450.3), "measured"
     return 1400.0, 6650.0, "fallback"   # B200_PROFILING.md fallback (sustained GEMM, copy)
+
+
+def kernel_source_digest(*names):
+    """sha256 over the named csrc files: ties a committed ncu capture to the kernel sources it was taken from."""
+    h = hashlib.sha256()
+    for n in names:
+        h.update((PKG / "csrc" / n).read_bytes())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -100,55 +115,89 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference arm (CPU)
-def cpu_reference_step(state):
-    """One denoise step of ONE C2-shaped utterance with the oracle port of the reference
-    (fp32 denoiser forward of base.py + dense fp16 p_sample of ar_discrete.py), all host threads."""
-    from oracle import denoiser as on
-    sd, orc, text, proms, x_t, t = state["sd"], state["orc"], state["text"], state["proms"], state["x_t"], state["t"]
-    tt = torch.tensor([t])
-    logits = on.diffusion_logits(sd, text, proms, [x_t], tt, MODEL["n_heads"], MODEL["n_layers"])[0]
-    lg = logits.to(torch.float16)                                   # (T_r, 8, K): reference p_sample needs fp16
-    noise = torch.rand(lg.shape)
-    tok_t = torch.full((lg.shape[0],), t)
-    samp, _ = orc.p_sample(lg, tok_t, x_t.to(torch.int32), noise)
-    state["x_t"] = samp
-    state["t"] = max(t - 1, 1)
+class CpuReference:
+    """One utterance of a workload's shape on the host cores.  kind "reference": the reference's own modules
+    staged in oracle/_ref (oracle/refarm.py: its Base stack + its p_sample with dense fp16 tables, its call
+    convention, its hard-coded 1025 classes); kind "port": the oracle restatement, only where oracle/_ref is
+    not staged."""
 
+    def __init__(self, wl, quarter=False):
+        from oracle import refarm
+        B, t_txt, t_prom, t_resp, timesteps, transition = WORKLOADS[wl]
+        torch.set_num_threads(os.cpu_count() or 1)
+        self.wl, self.t_resp, self.n_den = wl, t_resp, timesteps - 1
+        self.model = QUARTER if quarter else MODEL
+        text, proms = synth_utterance(0, t_txt, t_prom)
+        if refarm.available():
+            self.kind = "reference"
+            self.ref = refarm.ReferenceStep(self.model["d_model"], self.model["n_heads"], self.model["n_layers"],
+                                            timesteps, transition, text, proms, t_resp)
+            self.step = self.ref.step
+        else:
+            from oracle import denoiser as on
+            from oracle.d3pm import D3PM
+            self.kind = "port"
+            K = self.model["n_tokens"]
+            sd = on.random_state_dict(K, self.model["d_model"], self.model["n_layers"], timesteps + 1, n_resp_levels=8,
+                                      n_out=8 * K, seed=0, time_rows=timesteps + 1, bf16_round=False)
+            st = dict(x=torch.full((t_resp, 8), K // 2, dtype=torch.long), t=timesteps - 1)
+            orc = D3PM(timesteps, K, transition)
 
-def cpu_reference_setup(t_txt, t_prom, t_resp, timesteps, transition):
-    from oracle import denoiser as on
-    from oracle.d3pm import D3PM
-    torch.set_num_threads(os.cpu_count() or 1)
-    K = MODEL["n_tokens"]
-    sd = on.random_state_dict(K, MODEL["d_model"], MODEL["n_layers"], timesteps + 1, n_resp_levels=8,
-                              n_out=8 * K, seed=0, time_rows=timesteps + 1, bf16_round=False)
-    text, proms = synth_batch(1, t_txt, t_prom, seed=1)
-    x_t = torch.full((t_resp, 8), K // 2, dtype=torch.long)
-    return dict(sd=sd, orc=D3PM(timesteps, K, transition), text=text, proms=proms, x_t=x_t, t=timesteps - 1)
+            def step():
+                lg = on.diffusion_logits(sd, [text], [proms], [st["x"]], torch.tensor([st["t"]]), self.model["n_heads"],
+                                         self.model["n_layers"])[0].to(torch.float16).view(1, -1, K)
+                samp, _ = orc.p_sample(lg, torch.tensor([st["t"]]), st["x"].reshape(1, -1).to(torch.int32),
+                                       torch.rand(1, lg.shape[1], K))
+                st["x"], st["t"] = samp.view(-1, 8), max(st["t"] - 1, 1)
+            self.step = step
+        self.cores = torch.get_num_threads()
+
+    def time_steps(self, n, warmup=1):
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            self.step()
+        return (time.perf_counter() - t0) / n
+
+    def tokens_per_s(self, step_s):
+        return self.t_resp * 8 / (step_s * self.n_den)
+
+    def sample_text(self, n, step_s):
+        what = ("the reference's own modules (oracle/_ref: Base stack fp32 + p_sample with dense fp16 tables, 1025 classes)"
+                if self.kind == "reference" else "oracle port of the reference (fp32 denoiser + dense fp16 p_sample)")
+        size = "quarter model" if self.model is QUARTER else "full model"
+        return (f"{what}; ONE utterance of the {self.wl} shape, {size}; {n} of its {self.n_den} denoise steps timed "
+                f"({step_s:.3f} s each); tokens/s = {self.t_resp * 8} / ({self.n_den} x step time)")
 
 
 def run_reference(args, wl):
-    B, t_txt, t_prom, t_resp, timesteps, transition = WORKLOADS[wl]
+    """`--impl reference`: each bench step = ONE denoise step of ONE utterance of the workload's shape on the host
+    cores (a bounded sample: the whole batch would take hours), extrapolated to the utterance's full reverse loop;
+    plus BASELINE configs[0] (C1: quarter model, 225 frames, 50 steps) run IN FULL, as BASELINE.md §5 promises."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    state = cpu_reference_setup(t_txt, t_prom, t_resp, timesteps, transition)
-    for _ in range(args.warmup):
-        cpu_reference_step(state)
+    B, t_txt, t_prom, t_resp, timesteps, transition = WORKLOADS[wl]
+    ref = CpuReference(wl)
+    dt = ref.time_steps(args.steps, warmup=args.warmup)
+    value = ref.tokens_per_s(dt)
+    c1 = CpuReference("c1", quarter=True)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_reference_step(state)
-    dt = (time.perf_counter() - t0) / args.steps
-    n_den = timesteps - 1
-    value = t_resp * 8 / (dt * n_den)          # tokens of one utterance / time of its full reverse loop
-    cores = torch.get_num_threads()
-    sample = (f"1 utterance of the {wl} shape (T={t_txt + t_prom + t_resp + 2}), each step = 1 of its {n_den} denoise "
-              f"steps (fp32 denoiser forward + dense fp16 p_sample); tokens/s = {t_resp * 8} / ({n_den} x step time)")
+    for _ in range(c1.n_den):
+        c1.step()
+    c1_s = time.perf_counter() - t0
+    cfg = config_dict(wl, args.gpus)
+    cfg["reference_sample"] = ("ONE utterance of this shape, one denoise step per bench step (not the whole batch); "
+                               "value = its tokens / (denoise steps x measured step time)")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(wl, args.gpus),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                             "sample": ref.sample_text(args.steps, dt)},
+            "c1_full": {"workload": "c1: quarter model (d=256, 4 heads, 12 layers), 1 utterance x (30 phones + 225 prompt "
+                                    "frames + 225 frames), 50 denoise steps, uniform — run in full",
+                        "seconds": c1_s, "value": 225 * 8 / c1_s, "unit": UNIT, "kind": c1.kind, "cores": c1.cores},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -162,14 +211,14 @@ def config_dict(wl, n_gpus):
             "l2_policy": "per-step working set (activations > 1 GB per GPU at every N) exceeds the 126 MB L2; no flush needed",
             "operands": "16-bit tensor-core operands, fp32 accumulate: bf16 everywhere except the classifier GEMM "
                         "(fp16 rows and weights); fp32 residual stream",
-            "parallelism": f"utterance-sharded x{n_gpus}, one final all-gather"}
+            "parallelism": f"utterance-sharded x{n_gpus} (vall_e.b200.shard.generate_sharded), one final all-gather"}
 
 
 # ----------------------------------------------------------------------------- our arm
 def run_ours(args, wl):
     import torch.distributed as dist
     from vall_e.b200 import lib as L
-    from vall_e.b200.shard import partition, utterance_cost
+    from vall_e.b200.shard import generate_sharded
     from vall_e.vall_e.diffusion import Diffusion
 
     B, t_txt, t_prom, t_resp, timesteps, transition = WORKLOADS[wl]
@@ -191,100 +240,98 @@ def run_ours(args, wl):
             torch.nn.init.normal_(sub.norm.emb.weight, std=0.02)
     model = model.to(dev)
     eng = model.engine()
-
-    costs = [utterance_cost(t_txt, t_prom, t_resp)] * B
-    mine = partition(costs, world)[rank]
-    n_local = len(mine)
-    resp_lens = [t_resp] * n_local
+    resp_lens = [t_resp] * B
     n_total = args.warmup + args.steps
-    # host batches in pinned memory (e2e arm) — a different synthetic batch every step
-    batches = []
+
+    # Every rank holds the full (tiny) token lists of every step, built from GLOBAL utterance ids, in pinned
+    # memory; generate_sharded picks this rank's shard.  gid of utterance i of step s = s * B + i.
+    host, devb = [], []
     for s in range(n_total):
-        text, proms = synth_batch(n_local, t_txt, t_prom, seed=1000 * (1 + rank) + s)
-        batches.append(([t.pin_memory() for t in text], [p.pin_memory() for p in proms],
-                        [s * B + i for i in mine]))
+        utts = [synth_utterance(s * B + i, t_txt, t_prom) for i in range(B)]
+        host.append(([u[0].pin_memory() for u in utts], [u[1].pin_memory() for u in utts]))
+
+    def gen_fn(step):
+        def fn(text_sub, proms_sub, lens_sub, mine):
+            return model.generate_audio(text_sub, proms_sub, resp_lens=lens_sub, seed=args.seed,
+                                        gids=[step * B + i for i in mine])
+        return fn
 
     def sync_all():
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
 
-    def max_over_ranks(ms):
+    def reduce_ranks(ms, op):
         if world == 1:
             return ms
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def gather_codes(x_t):
-        """the one collective of the path: all-gather of the generated codes (int16 bytes)"""
+    def all_ranks(ms):
         if world == 1:
-            return x_t
-        send = x_t.to(torch.int16).view(torch.uint8).view(-1)
-        n_max = (B + world - 1) // world * t_resp * 8 * 2
-        buf = torch.zeros(n_max, dtype=torch.uint8, device=dev)
-        buf[: send.numel()] = send
-        out = torch.empty(world * n_max, dtype=torch.uint8, device=dev)
-        dist.all_gather_into_tensor(out, buf)
-        return out
+            return [ms]
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        out = torch.empty(world, device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(out, t)
+        return [float(v) for v in out.tolist()]
 
-    # ---------------- device-resident arm: inputs already in HBM when the clock starts
-    ses = model._session(batches[0][0], batches[0][1], resp_lens, batches[0][2])
-    table = model._table(dev)
-    tr = L.ABSORBING if transition == "absorbing" else L.UNIFORM
-
-    def device_step(i):
-        ses.load([t.to(dev) for t in batches[i][0]], [p.to(dev) for p in batches[i][1]], None)   # untimed staging happens before
-        ses.x_t.fill_(model.mask_id)
-
-    def timed_device_step():
-        ses.run(table, timesteps, tr, noise=L.NOISE_PHILOX, seed=args.seed, use_graph=True)
-        gather_codes(ses.x_t)
-
-    for i in range(args.warmup):
-        device_step(i)
-        timed_device_step()
-    sync_all()
-    launches0 = eng.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    with ClockSampler(local) as clocks:
+    def timed_arm(batches, to_host):
+        """W warm-up + K timed passes of generate_sharded; returns (mean step ms on this rank, mean local
+        (pre-gather) ms on this rank, packed codes of the last step on the host, wall seconds)."""
+        for i in range(args.warmup):
+            generate_sharded(gen_fn(i), batches[i][0], batches[i][1], resp_lens, device=dev, packed=True)
         sync_all()
-        t_wall0 = time.perf_counter()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        tim = [dict() for _ in range(args.steps)]
+        last = None
+        t0 = time.perf_counter()
         for k in range(args.steps):
-            device_step(args.warmup + k)      # restage inputs on device (outside the event bracket)
+            i = args.warmup + k
+            if to_host:
+                sync_all()                       # e2e: every step starts from idle, like a fresh request
             ev[k][0].record()
-            timed_device_step()
+            packed, _ = generate_sharded(gen_fn(i), batches[i][0], batches[i][1], resp_lens, device=dev, packed=True,
+                                         timing=tim[k])
+            if to_host:
+                last = packed.to("cpu", non_blocking=False)      # the step's result, read back by the caller
+            else:
+                last = packed
             ev[k][1].record()
         sync_all()
-        t_wall = time.perf_counter() - t_wall0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    ms = max_over_ranks(sum(step_ms) / len(step_ms))
-    launches = (eng.launches - launches0)
+        wall = time.perf_counter() - t0
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        local_ms = [t["local_start"].elapsed_time(t["local_end"]) for t in tim]
+        return sum(step_ms) / len(step_ms), sum(local_ms) / len(local_ms), last.cpu(), wall
+
+    # ---------------- device-resident arm: the batches are already in HBM when the clock starts
+    for s in range(n_total):
+        devb.append(([t.to(dev) for t in host[s][0]], [p.to(dev) for p in host[s][1]]))
+    sync_all()
+    launches0 = eng.launches
+    with ClockSampler(local) as clocks:
+        ms_rank, local_rank, codes_dev_arm, t_wall = timed_arm(devb, to_host=False)
+    launches = eng.launches - launches0
+    ms = reduce_ranks(ms_rank, dist.ReduceOp.MAX if world > 1 else None)
+    rank_local_ms = all_ranks(local_rank)
+    rank_step_ms = all_ranks(ms_rank)
     tokens_per_step = B * t_resp * 8
     value = tokens_per_step / (ms / 1e3)
+    del devb
 
-    # ---------------- end-to-end arm: public API, pinned host inputs -> host codes, every step
-    for i in range(min(1, args.warmup)):
-        model.generate_audio(batches[i][0], batches[i][1], resp_lens=resp_lens, seed=args.seed, gids=batches[i][2], to_host=True)
-    sync_all()
-    e2e_ms = []
-    for k in range(args.steps):
-        bt, bp, gid = batches[args.warmup + k]
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sync_all()
-        a.record()
-        codes = model.generate_audio(bt, bp, resp_lens=resp_lens, seed=args.seed, gids=gid, to_host=True)
-        if world > 1:
-            gather_codes(ses.x_t)
-        b.record()
-        torch.cuda.synchronize(dev)
-        e2e_ms.append(a.elapsed_time(b))
-    e2e = max_over_ranks(sum(e2e_ms) / len(e2e_ms))
+    # ---------------- end-to-end arm: pinned host inputs -> gathered codes on the host, every step
+    e2e_rank, _, codes_host, _ = timed_arm(host, to_host=True)
+    e2e = reduce_ranks(e2e_rank, dist.ReduceOp.MAX if world > 1 else None)
     h2d = int(model.last_h2d_bytes)
-    d2h = int(n_local * t_resp * 8 * 4)
+    d2h = int(codes_host.numel() * 2)                  # int16 codes of ALL utterances, read back on every rank
+    sha = hashlib.sha256(codes_host.contiguous().numpy().tobytes()).hexdigest()
+    same_codes = bool(torch.equal(codes_host, codes_dev_arm))       # the two arms generate the same batch
 
     # ---------------- roofline of the dominant kernel (tcgen05 GEMM), measured live: one eager
-    # pass of the same batch with CUDA events around every GEMM / attention launch
+    # pass over this rank's shard of the last batch with CUDA events around every GEMM / attention launch
+    ses = next(iter(eng._sessions.values()))
+    table = model._table(dev)
+    tr = L.ABSORBING if transition == "absorbing" else L.UNIFORM
     eng.profile = []
     ses.x_t.fill_(model.mask_id)
     prof_steps = 2
@@ -313,25 +360,31 @@ def run_ours(args, wl):
     at = agg.get("attn", [0.0, 1.0, 1])
     gemm_tf = g[0] / (g[1] * 1e-3) / 1e12
     attn_tf = at[0] / (at[1] * 1e-3) / 1e12
-    step_total_ms = ms / (timesteps - 1)
-    traffic = None      # dram bytes per launch of the dominant GEMM from one committed `ncu --set full` capture
-    tf = ROOT / "profiles" / "r1_gemm_traffic.json"
+    step_total_ms = local_rank / (timesteps - 1)
+    # dram bytes per launch of the largest GEMM (FFN1) from the committed `ncu --set full` capture — reported
+    # only while the kernel sources are the ones the capture was taken from
+    traffic, traffic_note = None, "no ncu capture committed for the current GEMM sources"
+    tf = ROOT / "profiles" / "gemm_traffic.json"
     if tf.exists():
         tj = json.loads(tf.read_text())
-        traffic = tj.get("bytes_per_launch")
+        if tj.get("kernel_source_digest") == kernel_source_digest("gemm_tcgen05.cu", "common.cuh"):
+            traffic = tj.get("bytes_per_launch")
+            traffic_note = (f"dram bytes of one FFN1 launch (largest GEMM) from {tj.get('capture')}; algorithmic "
+                            f"{tj.get('algorithmic_bytes')}; capture and build share kernel_source_digest "
+                            f"{tj.get('kernel_source_digest')}")
+        else:
+            traffic_note = "profiles/gemm_traffic.json was captured from other GEMM sources (digest mismatch): not reported"
     roofline = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (QKV/out/FFN1/FFN2) + head_sample_kernel (classifier)",
                 "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": gemm_tf / peak_tf,
                 "peak_source": f"{peak_src} bf16_tflops_sustained",
                 "peak_note": "cuBLAS bf16 back to back for 4 s at the pool's power cap; the launches here are timed one by "
                              "one inside an eager pass of the step, so a lightly loaded box can exceed it (burst figure 1632)",
-                "traffic": traffic,
-                "traffic_note": "dram bytes of one FFN1 launch (largest GEMM) from profiles/r1_gemm_traffic.json; algorithmic 2.70 GB",
+                "traffic": traffic, "traffic_note": traffic_note,
                 "avg_launch_ms": g[1] / g[2], "launches_timed": g[2],
                 "share_of_denoise_step": (g[1] / prof_steps) / step_total_ms,
                 "attention": {"kernel": "flash_attn_kernel", "achieved": attn_tf, "unit": "TFLOP/s",
                               "frac": attn_tf / peak_tf, "avg_launch_ms": at[1] / at[2],
                               "share_of_denoise_step": (at[1] / prof_steps) / step_total_ms}}
-    # the HBM-bound kernels of the step beside it (algorithmic bytes / launch time / measured copy bandwidth)
     if hsamp:
         roofline["head_sample"] = {"kernel": "head_sample_kernel (classifier GEMM + D3PM reverse step, one launch)",
                                    "bound": "tensor", "achieved": hsamp[0] / (hsamp[1] * 1e-3) / 1e12,
@@ -351,12 +404,12 @@ def run_ours(args, wl):
     latency = None
     if rank == 0:
         b1, tt1, tp1, tr1, _, _ = WORKLOADS["c2"]
-        text1, proms1 = synth_batch(1, tt1, tp1, seed=7)
-        ses1 = model._session([t.to(dev) for t in text1], [p.to(dev) for p in proms1], [tr1], [0])
+        text1, proms1 = synth_utterance(7, tt1, tp1)
+        ses1 = model._session([text1.to(dev)], [proms1.to(dev)], [tr1], [0])
         ses1.x_t.fill_(model.mask_id)
         ses1.run(table, timesteps, tr, noise=L.NOISE_PHILOX, seed=args.seed, use_graph=True)   # captures the step graph
         lat = []
-        for _ in range(40):
+        for _ in range(60):
             ses1.t_utt.fill_(timesteps // 2)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
@@ -364,25 +417,28 @@ def run_ours(args, wl):
             b.record()
             torch.cuda.synchronize(dev)
             lat.append(a.elapsed_time(b))
-        lat = sorted(lat[10:])
-        latency = {"p50_denoise_step_ms": lat[len(lat) // 2], "p90_denoise_step_ms": lat[int(len(lat) * 0.9)],
-                   "workload": f"c2: batch 1, T={tt1 + tp1 + tr1 + 2} rows ({tr1} frames x 8 levels), one graph replay per step",
-                   "tokens_per_sec_batch1": tr1 * 8 / (lat[len(lat) // 2] * 1e-3 * (timesteps - 1))}
+        lat = sorted(lat[20:])
+        T1 = tt1 + tp1 + tr1 + 2
+        d_, nl_ = MODEL["d_model"], MODEL["n_layers"]
+        flops1 = nl_ * (24 * T1 * d_ * d_ + 4 * T1 * T1 * d_) + 2 * tr1 * d_ * 8 * MODEL["n_tokens"]
+        p50 = lat[len(lat) // 2]
+        latency = {"p50_denoise_step_ms": p50, "p90_denoise_step_ms": lat[int(len(lat) * 0.9)],
+                   "workload": f"c2: batch 1, T={T1} rows ({tr1} frames x 8 levels), one graph replay per step",
+                   "tokens_per_sec_batch1": tr1 * 8 / (p50 * 1e-3 * (timesteps - 1)),
+                   "roofline": {"bound": "tensor", "flop_per_step": flops1, "achieved": flops1 / (p50 * 1e-3) / 1e12,
+                                "peak": measured_peaks()[0], "unit": "TFLOP/s",
+                                "frac": flops1 / (p50 * 1e-3) / 1e12 / measured_peaks()[0],
+                                "note": "single utterance: every kernel of the step is one partial wave; the floor is "
+                                        "~0.27 ms of MMAs + 52 us of weight reads"}}
 
-    # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample of the oracle port
+    # ---------------- CPU baseline beside it (rank 0, N=1 only): bounded sample on the host cores
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        state = cpu_reference_setup(t_txt, t_prom, t_resp, timesteps, transition)
-        cpu_reference_step(state)
-        t0 = time.perf_counter()
+        ref = CpuReference(wl)
         n = 2
-        for _ in range(n):
-            cpu_reference_step(state)
-        dt = (time.perf_counter() - t0) / n
-        cpu_baseline = {"value": t_resp * 8 / (dt * (timesteps - 1)), "unit": UNIT, "cores": torch.get_num_threads(),
-                        "kind": "port",
-                        "sample": f"oracle port of the reference, 1 utterance of this shape, {n} of {timesteps - 1} denoise "
-                                  f"steps timed ({dt:.2f} s each), tokens/s = {t_resp * 8} / ({timesteps - 1} x step)"}
+        dt = ref.time_steps(n, warmup=1)
+        cpu_baseline = {"value": ref.tokens_per_s(dt), "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+                        "sample": ref.sample_text(n, dt)}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -392,6 +448,13 @@ def run_ours(args, wl):
                 "clocks": clocks.summary(),
                 "e2e": {"value": tokens_per_step / (e2e / 1e3), "unit": UNIT, "ms_per_step": e2e,
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "codes_sha256": sha, "codes_note": "sha256 of the int16 codes of the LAST timed batch, all utterances in "
+                                                   "global order; utterances and Philox noise are keyed by global id, so it "
+                                                   "must be identical at N = 1, 2, 4, 8 for equal --steps/--warmup/--seed",
+                "codes_equal_between_arms": same_codes,
+                "per_rank": {"step_ms": rank_step_ms, "local_ms": rank_local_ms,
+                             "local_ms_min": min(rank_local_ms), "local_ms_max": max(rank_local_ms),
+                             "note": "step = generate_sharded incl. the all-gather; local = this rank's reverse loop only"},
                 "gpu_launches": launches, "roofline": roofline, "latency": latency, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -154,11 +154,21 @@ enum {
 };
 
 /* Q: q_sample (ar_discrete.py:467-487): x_t = argmax_j(log(Qbar_t[x0, j] + eps) + g_j) * mask,
- * g = -log(-log(clamp(u, tiny, 1))).  Bit-exact against the reference for supplied uniforms
- * (absorbing tables).  x0, x_out, mask int32 (n_tok); t_tok int32 (n_tok) timestep per token. */
+ * g = -log(-log(clamp(u, tiny, 1))).  Bit-exact against the reference for supplied uniforms with the
+ * absorbing tables; for the uniform transition see vb200_q_sample_dense below.  x0, x_out, mask int32 (n_tok); t_tok int32 (n_tok) timestep per token. */
 int vb200_q_sample(int32_t* x_out, const int32_t* x0, const int32_t* t_tok, const int32_t* mask,
                    const float* uniforms, const float* table, int32_t n_tok, int32_t K,
                    int32_t S, vb200_transition tr, vb200_stream_t stream);
+
+/* Q against the caller's own DENSE table: log_qbar_f16 = fp16 log(Qbar_t + eps), shape (S, K, K), i.e. the
+ * logits ar_discrete.py:482 forms from `q_mats` (ar_discrete.py:270-275).  Row x0 of it replaces the
+ * per-timestep scalars, so the result is bit-exact against whichever dense chain product the caller holds.
+ * Needed for the UNIFORM transition only: its K-term fp16 sums round differently per entry depending on the
+ * summation order of the GEMM that built the table (CPU BLAS here, cuBLAS in the reference's constructor),
+ * so no scalar table reproduces the last bit (absorbing products have <= 2 non-zero terms and are exact). */
+int vb200_q_sample_dense(int32_t* x_out, const int32_t* x0, const int32_t* t_tok, const int32_t* mask,
+                         const float* uniforms, const void* log_qbar_f16, int32_t n_tok, int32_t K,
+                         int32_t S, vb200_stream_t stream);
 
 /* q_sample with in-kernel noise (training forwards, ar_discrete.py:651-653): the same categorical
  * law — weights exp(fp16 log(Qbar_t[x0, j] + eps)) — drawn in O(1) per token from one Philox

@@ -5,7 +5,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 PKG = ROOT / "tts-with-diffusion-model_b200"
-for p in (str(ROOT), str(PKG), str(ROOT / "tests" / "golden")):
+for p in (str(ROOT), str(PKG), str(ROOT / "tests" / "golden"), str(ROOT / "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 

@@ -18,6 +18,30 @@ def L():
     return lib
 
 
+def _oracle_law(orc, logits16_row, x_t, t):
+    """softmax of the ORACLE's posterior logits (reference q_posterior_logits, dense fp16 tables) for one
+    token: the law every sampler of this library is tested against."""
+    lg = logits16_row.view(1, 1, -1).to(torch.float16)
+    post = orc.q_posterior_logits(lg, torch.tensor([[x_t]], dtype=torch.int32), torch.tensor([t]))
+    return torch.softmax(post.double(), -1).view(-1)
+
+
+def _assert_draws_follow(draws, law, ctx):
+    """chi-square of the observed class counts against ``law`` (cells with expectation <= 5 pooled)."""
+    n, K = draws.numel(), law.numel()
+    counts = torch.bincount(draws.view(-1).cpu().long(), minlength=K).double()
+    expected = law * n
+    keep = expected > 5
+    chi2 = (((counts - expected) ** 2) / expected)[keep].sum().item()
+    cells = int(keep.sum().item())
+    rest_obs, rest_exp = counts[~keep].sum().item(), expected[~keep].sum().item()
+    if rest_exp > 5:
+        chi2 += (rest_obs - rest_exp) ** 2 / rest_exp
+        cells += 1
+    dof = max(cells - 1, 1)
+    assert chi2 < dof + 6 * math.sqrt(2 * dof), (ctx, chi2, dof)
+
+
 def _rand_bf16(shape, seed, scale=1.0):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(*shape, generator=g) * scale).to(torch.bfloat16).to(DEV)
@@ -142,18 +166,44 @@ def test_q_sample_bit_exact_vs_oracle(L, d3pm_pair):
     mask[-5:] = 0
     noise = torch.from_numpy(detrand.uniform(12, (B, W, K)))
     ref = orc.q_sample(x0, t, mask, noise)
-    out = torch.empty(B * W, dtype=torch.int32, device=DEV)
-    L.q_sample(out, x0.to(DEV, torch.int32).view(-1), t.to(DEV, torch.int32).repeat_interleave(W),
-               mask.to(DEV, torch.int32).repeat(B), noise.to(DEV), table, K,
-               L.ABSORBING if tr == "absorbing" else L.UNIFORM)
-    got = out.cpu().view(B, W).long()
+    got = _q_sample_cuda(L, tr, table, S, K, x0, t, mask, noise)
     mism = (got != ref).sum().item()
+    assert mism == 0, f"{tr}: {mism} of {B * W} tokens differ"
+
+
+def _q_sample_cuda(L, tr, table, S, K, x0, t, mask, noise):
+    """absorbing: per-timestep scalars (the fp16 chain product is exactly rank-structured);
+    uniform: the dense fp16 log(Qbar + eps) table (its K-term sums are not — DESIGN.md §2)."""
+    from vall_e.vall_e import d3pm as pd
+    B, W = x0.shape
+    out = torch.empty(B * W, dtype=torch.int32, device=DEV)
+    args = (out, x0.to(DEV, torch.int32).view(-1).contiguous(), t.to(DEV, torch.int32).repeat_interleave(W),
+            mask.to(DEV, torch.int32).expand(B, W).contiguous().view(-1), noise.to(DEV).contiguous())
     if tr == "absorbing":
-        assert mism == 0, f"{mism} of {B * W} tokens differ"
+        L.q_sample(*args, table, K, L.ABSORBING)
     else:
-        # the reference's uniform fp16 chain product is position dependent by one fp16 ulp
-        # ("uniform tables"), so a scalar table cannot be bit-exact for every token
-        assert mism <= 0.02 * B * W, f"{mism} of {B * W} tokens differ"
+        L.q_sample_dense(*args, pd.dense_log_qbar(S, K, "uniform").to(DEV))
+    return out.cpu().view(B, W).long()
+
+
+def test_q_sample_bit_exact_sweep_100k_tokens(L, d3pm_pair):
+    """north_star: forward noising from supplied uniforms is bit-exact.  128 000 tokens, every timestep
+    0..S-1, both transitions: ZERO tokens may differ from the oracle (reference ar_discrete.py:467-487)."""
+    import detrand
+    tr, orc, table, S, K = d3pm_pair
+    W, total = 160, 0
+    t = torch.arange(S)
+    mask = torch.ones(W, dtype=torch.int64)
+    for rep in range(8):
+        x0 = torch.from_numpy(detrand.integers(300 + rep, 0, K, (S, W)))
+        x0[:, rep] = K // 2
+        noise = torch.from_numpy(detrand.uniform(400 + rep, (S, W, K)))
+        ref = orc.q_sample(x0, t, mask, noise)
+        got = _q_sample_cuda(L, tr, table, S, K, x0, t, mask, noise)
+        mism = int((got != ref).sum())
+        assert mism == 0, f"{tr}: {mism} of {S * W} tokens differ (rep {rep})"
+        total += S * W
+    assert total >= 100_000
 
 
 def test_posterior_vs_oracle(L, d3pm_pair):
@@ -239,11 +289,18 @@ def test_posterior_golden_fixture(L, golden_dir):
         mask = torch.ones(W, dtype=torch.int32)
         mask[-3:] = 0
         nq = torch.from_numpy(detrand.uniform(seed + 1, (B, W, K)))
-        xo = torch.empty(B * W, dtype=torch.int32, device=DEV)
-        L.q_sample(xo, x0.to(DEV, torch.int32).view(-1), t.to(DEV, torch.int32).repeat_interleave(W),
-                   mask.to(DEV).repeat(B), nq.to(DEV), table, K, code)
-        mism = (xo.cpu().view(B, W) != torch.from_numpy(z["q_xt"])).sum().item()
-        assert mism == 0 if tr == "absorbing" else mism <= 0.02 * B * W, mism
+        xo = _q_sample_cuda(L, tr, table, S, K, x0, t, mask, nq)
+        mism = (xo != torch.from_numpy(z["q_xt"]).long()).sum().item()
+        if mism and tr == "uniform":
+            # The fixture was made where the reference ran; the uniform chain product's last bit depends on
+            # that CPU's fp16 GEMM summation order.  Only if THIS box's oracle does not reproduce the fixture
+            # either may the kernel differ from it — and then it must equal the oracle on this box's tables.
+            from oracle.d3pm import D3PM
+            here = D3PM(S, K, tr).q_sample(x0, t, mask.long(), nq)
+            assert not torch.equal(here, torch.from_numpy(z["q_xt"]).long()), "oracle matches the fixture, kernel does not"
+            assert torch.equal(xo, here)
+        else:
+            assert mism == 0, (tr, mism)                # the reference's own q_sample output, bit for bit
 
 
 def test_philox_sampling_matches_posterior_distribution(L):
@@ -251,8 +308,9 @@ def test_philox_sampling_matches_posterior_distribution(L):
     from vall_e.vall_e import d3pm as pd
     S, K, n = 50, 64, 40000
     table = pd.scalar_table(S, K, "absorbing").to(DEV)
+    from oracle.d3pm import D3PM
     g = torch.Generator().manual_seed(3)
-    row = (torch.randn(K, generator=g) * 1.5)
+    row = (torch.randn(K, generator=g) * 1.5).half().float()          # fp16-representable: the oracle takes fp16 logits
     logits = row.repeat(n, 1).to(DEV)
     x_t = torch.full((n,), K // 2, dtype=torch.int32, device=DEV)
     utt = torch.zeros(1, L.U_STRIDE, dtype=torch.int32, device=DEV)
@@ -262,13 +320,7 @@ def test_philox_sampling_matches_posterior_distribution(L):
     post = torch.empty(n, K, dtype=torch.float32, device=DEV)
     L.posterior_sample_from_logits(out, post, logits, K, x_t, row_utt, t_utt, utt, table, n, 1, K, L.ABSORBING,
                                    L.NOISE_PHILOX, seed=77)
-    p = torch.softmax(post[0].cpu().double(), -1)
-    counts = torch.bincount(out.cpu().long(), minlength=K).double()
-    expected = p * n
-    keep = expected > 5
-    chi2 = (((counts - expected) ** 2) / expected)[keep].sum().item()
-    dof = int(keep.sum().item()) - 1
-    assert chi2 < dof + 6 * math.sqrt(2 * dof), (chi2, dof)
+    _assert_draws_follow(out, _oracle_law(D3PM(S, K, "absorbing"), row, K // 2, 20), "generic kernel, K=64")
     out2 = torch.empty_like(out)
     L.posterior_sample_from_logits(out2, None, logits, K, x_t, row_utt, t_utt, utt, table, n, 1, K, L.ABSORBING,
                                    L.NOISE_PHILOX, seed=77)
@@ -305,29 +357,22 @@ def test_fast_posterior_kernel_matches_generic(L, transition, K):
     clear = ((top2[:, 0] - top2[:, 1]) > 1e-3).view(rows, levels)
     assert clear.float().mean().item() > 0.9
     assert torch.equal(fast[clear], slow[clear])
-    # (b) distribution of the inverse-CDF sampler, masked and unmasked current token
-    n = 30000
+    # (b) distribution of the inverse-CDF sampler against the ORACLE's posterior law, masked and unmasked
+    # current token, early / middle / last timestep
+    from oracle.d3pm import D3PM
+    orc = D3PM(S, K, transition)
+    n = 40000
     row = (torch.randn(K, generator=g) * 2.0).half()
     lg = row.repeat(n, 1).to(DEV)
-    for xt_val in (K // 2, 3):
-        xt = torch.full((n, 1), xt_val, dtype=torch.int32, device=DEV)
-        ru = torch.zeros(n, dtype=torch.int32, device=DEV)
-        tu = torch.tensor([17], dtype=torch.int32, device=DEV)
-        u1 = torch.zeros(1, L.U_STRIDE, dtype=torch.int32, device=DEV)
-        out = torch.empty(n, 1, dtype=torch.int32, device=DEV)
-        pp = torch.empty(n, K, dtype=torch.float32, device=DEV)
-        L.posterior_sample_from_logits(out, None, lg, K, xt, ru, tu, u1, table, n, 1, K, code, L.NOISE_PHILOX, seed=5)
-        L.posterior_sample_from_logits(torch.empty_like(out), pp, lg, K, xt, ru, tu, u1, table, n, 1, K, code, L.NOISE_GREEDY)
-        p = torch.softmax(pp[0].double().cpu(), -1)
-        counts = torch.bincount(out.view(-1).cpu().long(), minlength=K).double()
-        expected = p * n
-        keep = expected > 5
-        chi2 = (((counts - expected) ** 2) / expected)[keep].sum().item()
-        rest_obs, rest_exp = counts[~keep].sum().item(), expected[~keep].sum().item()
-        if rest_exp > 5:
-            chi2 += (rest_obs - rest_exp) ** 2 / rest_exp
-        dof = max(int(keep.sum().item()), 2)
-        assert chi2 < dof + 6 * math.sqrt(2 * dof), (transition, K, xt_val, chi2, dof)
+    for t_val in (1, 17, S - 1):
+        for xt_val in (K // 2, 3):
+            xt = torch.full((n, 1), xt_val, dtype=torch.int32, device=DEV)
+            ru = torch.zeros(n, dtype=torch.int32, device=DEV)
+            tu = torch.tensor([t_val], dtype=torch.int32, device=DEV)
+            u1 = torch.zeros(1, L.U_STRIDE, dtype=torch.int32, device=DEV)
+            out = torch.empty(n, 1, dtype=torch.int32, device=DEV)
+            L.posterior_sample_from_logits(out, None, lg, K, xt, ru, tu, u1, table, n, 1, K, code, L.NOISE_PHILOX, seed=5)
+            _assert_draws_follow(out, _oracle_law(orc, row, xt_val, t_val), (transition, K, t_val, xt_val))
 
 
 def test_head_posterior_sample_fused_vs_separate_kernels(L):
@@ -385,26 +430,15 @@ def test_head_posterior_sample_fused_vs_separate_kernels(L):
     tu = torch.tensor([17], dtype=torch.int32, device=DEV)
     u1 = torch.zeros(1, L.U_STRIDE, dtype=torch.int32, device=DEV)
     scratch = torch.empty(n, K, dtype=torch.float16, device=DEV)
-    lg = torch.empty_like(scratch)
-    L.gemm_bf16(lg, head_in, W, bias, None, L.EPI_BIAS)
+    from oracle.d3pm import D3PM
+    orc = D3PM(S, K, "absorbing")
+    row16 = (row.float() @ W.float().cpu().t() + bias.cpu()).view(-1).to(torch.float16)    # the token's logits, as the oracle takes them
     for xt_val in (K // 2, 3):
         xt = torch.full((n, 1), xt_val, dtype=torch.int32, device=DEV)
         out = torch.empty(n, 1, dtype=torch.int32, device=DEV)
-        pp = torch.empty(n, K, dtype=torch.float32, device=DEV)
         L.head_posterior_sample(out, scratch, head_in, W, bias, xt, ru, tu, u1, table, 1, K, L.ABSORBING,
                                 L.NOISE_PHILOX, seed=5)
-        L.posterior_sample_from_logits(torch.empty_like(out), pp, lg, K, xt, ru, tu, u1, table, n, 1, K,
-                                       L.ABSORBING, L.NOISE_GREEDY)
-        p = torch.softmax(pp[0].double().cpu(), -1)
-        counts = torch.bincount(out.view(-1).cpu().long(), minlength=K).double()
-        expected = p * n
-        keep = expected > 5
-        chi2 = (((counts - expected) ** 2) / expected)[keep].sum().item()
-        rest_obs, rest_exp = counts[~keep].sum().item(), expected[~keep].sum().item()
-        if rest_exp > 5:
-            chi2 += (rest_obs - rest_exp) ** 2 / rest_exp
-        dof = max(int(keep.sum().item()), 2)
-        assert chi2 < dof + 6 * math.sqrt(2 * dof), (xt_val, chi2, dof)
+        _assert_draws_follow(out, _oracle_law(orc, row16, xt_val, 17), ("fused head", xt_val))
 
 
 @pytest.mark.parametrize("act", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])

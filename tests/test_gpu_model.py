@@ -454,6 +454,53 @@ def test_second_device_in_the_same_process():
             outs.append([c.cpu() for c in m.generate_audio([x.to(dev) for x in text], [x.to(dev) for x in proms],
                                                             resp_lens=[140, 301], seed=3)])
     assert all(torch.equal(a, b) for a, b in zip(*outs))
+    # a model on cuda:1 while the CURRENT device is cuda:0 (`python -m vall_e --device cuda:1`): the model
+    # classes switch device themselves, so the codes are the same again ...
+    assert torch.cuda.current_device() == 0
+    m, _ = _make(K, d, h, nl, S, "absorbing", seed=4)
+    m = m.to("cuda:1")
+    text, proms, _ = _batch(K, [(4, 10, 140), (6, 7, 301)], 9)
+    other = m.generate_audio([x.to("cuda:1") for x in text], [x.to("cuda:1") for x in proms], resp_lens=[140, 301], seed=3)
+    assert all(torch.equal(a.cpu(), b) for a, b in zip(other, outs[0]))
+    assert torch.cuda.current_device() == 0
+    # ... and a raw kernel call with tensors of another device is refused instead of dereferencing them on cuda:0
+    from vall_e.b200 import lib as L
+    t1 = torch.zeros(4, dtype=torch.int32, device="cuda:1")
+    with pytest.raises(L.VB200Error, match="current CUDA device"):
+        L.step_timesteps(t1, -1)
+    with pytest.raises(L.VB200Error, match="different devices"):
+        L.gather_rows_bf16(torch.empty(1, 64, dtype=torch.bfloat16, device="cuda:0"), torch.zeros(2, 64, device="cuda:1"),
+                           torch.zeros(1, dtype=torch.int32, device="cuda:0"))
+
+
+def test_wrong_ids_are_refused_before_any_launch():
+    """An id outside its table (e.g. the AR stop token 1024 in a K = 1024 model) raises IndexError, as the
+    reference's F.one_hot / nn.Embedding do, instead of an out-of-bounds read in the gather kernel."""
+    K, d, h, nl, S = 64, 64, 1, 1, 6
+    m, _ = _make(K, d, h, nl, S, "absorbing", seed=8)
+    text, proms, xt = _batch(K, [(3, 5, 9)], 2)
+    bad = [xt[0].clone()]
+    bad[0][2, 3] = K
+    with pytest.raises(IndexError):
+        m.generate_audio([x.to(DEV) for x in text], [x.to(DEV) for x in proms], [x.to(DEV) for x in bad])
+    with pytest.raises(IndexError):
+        m.generate_audio([x.to(DEV) for x in text], [(proms[0] - 1).to(DEV)], resp_lens=[9])
+    with pytest.raises(IndexError):
+        m.p_sample(torch.zeros(1, 2, K, device=DEV), torch.tensor([1]), torch.tensor([[0, K]], device=DEV), greedy=True)
+
+
+def test_uniform_start_state_is_keyed_by_global_utterance_id():
+    """x_T of the uniform transition is drawn per utterance from (seed, global id): an utterance generated
+    alone, or in another batch order, gets the codes it gets inside the full batch (sharding invariance)."""
+    K, d, h, nl, S = 256, 128, 2, 2, 7
+    m, _ = _make(K, d, h, nl, S, "uniform", seed=4)
+    text, proms, _ = _batch(K, [(4, 10, 40), (6, 7, 77), (3, 3, 21)], 9)
+    text, proms = [x.to(DEV) for x in text], [x.to(DEV) for x in proms]
+    full = m.generate_audio(text, proms, resp_lens=[40, 77, 21], seed=5, gids=[10, 11, 12])
+    solo = m.generate_audio(text[1:2], proms[1:2], resp_lens=[77], seed=5, gids=[11])
+    rev = m.generate_audio(text[::-1], proms[::-1], resp_lens=[21, 77, 40], seed=5, gids=[12, 11, 10])
+    assert torch.equal(solo[0], full[1])
+    assert all(torch.equal(a, b) for a, b in zip(rev[::-1], full))
 
 
 def test_full_size_logits_vs_oracle():
@@ -524,3 +571,22 @@ def test_c1_config_reverse_loop_vs_oracle():
         checked += int(clear.sum())
         agree += int((got[clear] == ref[clear]).sum())
     assert checked > 0.8 * 8 * 225 * 8 and agree == checked, (agree, checked)
+
+
+def test_cli_main_end_to_end(tmp_path, monkeypatch):
+    """``python -m vall_e <text> <ref.wav> <out.wav> --ar-ckpt <Diffusion pickle>`` in-process, all the way to
+    the written file: prompt through the (stubbed) EnCodec wrapper of ``vall_e.emb.qnt``, phones through
+    ``vall_e.emb.g2p``, the reverse loop on the CUDA kernels, the codes back through ``qnt.decode_to_file``.
+    ``vall_e.emb`` executes the reference's own files where a checkout exists, else a stand-in checkout."""
+    from pathlib import Path
+    from cli_helpers import run_cli, standin_reference_emb
+    ref = Path("/root/reference")
+    if not (ref / "vall_e" / "emb" / "qnt.py").is_file():
+        ref = standin_reference_emb(tmp_path / "standin")
+    main, calls, out = run_cli(tmp_path, monkeypatch, "cuda", ref)
+    main()
+    assert out.exists()
+    dec = [c for c in calls if c[0] == "decode"]
+    assert dec and dec[-1][1] == (1, 8, 20)                 # (b q t): 20 frames x 8 levels went to the decoder
+    wr = [c for c in calls if c[0] == "write"]
+    assert wr and wr[-1][1] == str(out) and wr[-1][3] == 24_000

@@ -86,3 +86,31 @@ def test_denoiser_diffusion_matches_reference(golden_dir):
     rows = on.base_forward_logits(sd, text, proms, xt, t, int(z["n_heads"]), int(z["n_layers"]), time_t=t)
     for i in range(2):
         assert np.abs(rows[i].numpy() - z[f"logits{i}"]).max() < 5e-5
+
+
+def test_reference_arm_runs_the_staged_reference_modules():
+    """oracle/refarm.py (the CPU arm of bench.py): the reference's own modules from oracle/_ref — staged by
+    build() where the reference checkout exists — run one denoise step, and the oracle port reproduces their
+    logits on the same weights (fp32, <= 5e-5) and their posterior (bit-exact), live, not only through fixtures."""
+    from oracle import denoiser as on
+    from oracle import refarm
+    from oracle.d3pm import D3PM
+    if not refarm.stage():
+        pytest.skip("oracle/_ref not staged (no reference checkout on this box)")
+    g = torch.Generator().manual_seed(3)
+    text, proms = torch.randint(1, 1025, (7,), generator=g), torch.randint(0, 1025, (11, 8), generator=g)
+    S = 6
+    ref = refarm.ReferenceStep(64, 1, 2, S, "absorbing", text, proms, t_resp=13, seed=5)
+    x = torch.randint(0, 1025, (13, 8), generator=g)
+    lg = ref.logits(x, 4)
+    sd = {k: v.detach() for k, v in ref.gm.state_dict().items()}
+    mine = on.diffusion_logits(sd, [text], [proms], [x], torch.tensor([4]), 1, 2)[0]
+    assert (mine - lg).abs().max().item() <= 5e-5
+    orc = D3PM(S, refarm.K_REF, "absorbing")
+    assert torch.equal(orc.q_mats, ref.tab.q_mats) and torch.equal(orc.betas, ref.tab.betas)
+    l16 = lg.to(torch.float16).view(1, -1, refarm.K_REF)
+    xr = x.reshape(1, -1).to(torch.int32)
+    assert torch.equal(orc.q_posterior_logits(l16, xr, torch.tensor([4])),
+                       ref.tab.q_posterior_logits(l16, xr, torch.tensor([4]), x_start_logits=True))
+    out = ref.step()
+    assert out.shape == (13, 8) and 0 <= int(out.min()) and int(out.max()) < refarm.K_REF

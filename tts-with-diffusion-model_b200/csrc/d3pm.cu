@@ -38,10 +38,15 @@ __device__ __forceinline__ Best warp_best(Best b) {
 }
 
 // ---------------------------------------------------------------- Q: q_sample
+// DENSE: row x0 of the caller's own fp16 table log(Qbar_t + eps) (S, K, K) replaces the per-timestep
+// scalars — for the uniform transition, whose K-term fp16 chain product is not rank-structured to the
+// last bit (which entry rounds up depends on the summation order of the GEMM that built the table).
+template <bool DENSE>
 __global__ void __launch_bounds__(256) q_sample_kernel(
     int32_t* __restrict__ x_out, const int32_t* __restrict__ x0, const int32_t* __restrict__ t_tok,
     const int32_t* __restrict__ mask, const float* __restrict__ uniforms,
-    const float* __restrict__ table, int n_tok, int K, int S, int transition) {
+    const float* __restrict__ table, const __half* __restrict__ log_qbar, int n_tok, int K, int S,
+    int transition) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int tok = blockIdx.x * warps_per_block + (threadIdx.x >> 5); tok < n_tok;
@@ -49,16 +54,24 @@ __global__ void __launch_bounds__(256) q_sample_kernel(
     const int x = x0[tok];
     int t = t_tok[tok];
     t = min(max(t, 0), S - 1);
-    const float* tab = table + static_cast<size_t>(t) * VB200_TAB_STRIDE;
     const int m = K / 2;
     const bool absorbing = transition == VB200_ABSORBING;
-    const float l_keep = tab[VB200_TAB_LOG_KEEP], l_off = tab[VB200_TAB_LOG_OFF];
-    const float l_abs = tab[VB200_TAB_LOG_ABSORB], l_both = tab[VB200_TAB_LOG_BOTH];
+    float l_keep = 0.f, l_off = 0.f, l_abs = 0.f, l_both = 0.f;
+    const __half* row = nullptr;
+    if (DENSE) {
+      row = log_qbar + (static_cast<size_t>(t) * K + min(max(x, 0), K - 1)) * K;
+    } else {
+      const float* tab = table + static_cast<size_t>(t) * VB200_TAB_STRIDE;
+      l_keep = tab[VB200_TAB_LOG_KEEP]; l_off = tab[VB200_TAB_LOG_OFF];
+      l_abs = tab[VB200_TAB_LOG_ABSORB]; l_both = tab[VB200_TAB_LOG_BOTH];
+    }
     const float* u = uniforms + static_cast<size_t>(tok) * K;
     Best best{-INFINITY, 0x7fffffff};
     for (int j = lane; j < K; j += 32) {
       float lg;
-      if (absorbing) {
+      if (DENSE) {
+        lg = __half2float(row[j]);
+      } else if (absorbing) {
         if (x == m) lg = (j == m) ? l_both : l_off;           // row m of Qbar: [0 .. 1 .. 0]
         else lg = (j == x) ? l_keep : ((j == m) ? l_abs : l_off);
       } else {
@@ -644,8 +657,25 @@ extern "C" int vb200_q_sample(int32_t* x_out, const int32_t* x0, const int32_t* 
   int grid = (n_tok + wpb - 1) / wpb;
   const int cap = num_sms() * 32;
   if (grid > cap) grid = cap;
-  q_sample_kernel<<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      x_out, x0, t_tok, mask, uniforms, table, n_tok, K, S, static_cast<int>(tr));
+  q_sample_kernel<false><<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_out, x0, t_tok, mask, uniforms, table, nullptr, n_tok, K, S, static_cast<int>(tr));
+  VB_CHECK_CUDA(cudaGetLastError());
+  return VB200_OK;
+}
+
+extern "C" int vb200_q_sample_dense(int32_t* x_out, const int32_t* x0, const int32_t* t_tok,
+                                    const int32_t* mask, const float* uniforms, const void* log_qbar_f16,
+                                    int32_t n_tok, int32_t K, int32_t S, vb200_stream_t stream) {
+  if (n_tok == 0) return VB200_OK;
+  VB_REQUIRE(x_out && x0 && t_tok && uniforms && log_qbar_f16, "q_sample_dense: null pointer");
+  VB_REQUIRE(n_tok >= 0 && K >= 2 && S >= 1, "q_sample_dense: bad sizes n_tok=%d K=%d S=%d", n_tok, K, S);
+  const int wpb = 8;
+  int grid = (n_tok + wpb - 1) / wpb;
+  const int cap = num_sms() * 32;
+  if (grid > cap) grid = cap;
+  q_sample_kernel<true><<<grid, wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      x_out, x0, t_tok, mask, uniforms, nullptr, static_cast<const __half*>(log_qbar_f16), n_tok, K, S,
+      VB200_UNIFORM);
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;
 }

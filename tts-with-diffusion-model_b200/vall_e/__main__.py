@@ -3,9 +3,10 @@
 
 Stages, as in the reference: EnCodec-encode the prompt (reference ``emb/qnt.py``), phonemise the
 text (``emb/g2p.py``), first-stage model -> codes, NAR / decode, write audio.  EnCodec and g2p stay
-on the reference implementation (out of scope and excluded from timing, BASELINE.json), so this
-entry point needs the reference's ``vall_e.emb`` (encodec, g2p_en, soundfile) importable; the model
-checkpoints are whole-module pickles (reference ``export.py``) resolved through this package's
+on the reference implementation (out of scope and excluded from timing, BASELINE.json): ``vall_e.emb``
+executes the reference's own ``emb/qnt.py`` and ``emb/g2p.py`` from a checkout named by ``VALL_E_REF``
+(see ``vall_e/emb/__init__.py``; they need encodec, torchaudio, soundfile and g2p_en installed).  The
+model checkpoints are whole-module pickles (reference ``export.py``) resolved through this package's
 ``vall_e.vall_e.{ar,nar,diffusion}`` classes.
 
   --ar-ckpt may hold a ``Diffusion`` model (8 levels in one reverse loop; NAR is then skipped), the
@@ -54,9 +55,7 @@ def main():
     try:
         from .emb import g2p, qnt  # reference front/back ends (EnCodec 24 kHz @ 6 kbps, g2p_en)
     except ImportError as e:  # pragma: no cover - depends on optional third-party packages
-        raise SystemExit(
-            "python -m vall_e needs the reference's vall_e/emb package (encodec, g2p_en, soundfile) on the "
-            f"path for audio I/O; it is outside the accelerated path ({e})")
+        raise SystemExit(f"python -m vall_e: audio I/O unavailable — {e}")
 
     first = _load(args.ar_ckpt, args.device)
     symmap = first.phone_symmap

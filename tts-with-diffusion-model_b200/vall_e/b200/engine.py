@@ -94,19 +94,38 @@ class PackedWeights:
         self.w_cls = as_(sd["classifier.weight"], "head")
         self.b_cls = f32(sd["classifier.bias"])
         self.n_out = int(self.w_cls.shape[0])
-        self._pe = None
+        self._pe, self._pe_retired = None, []
         self.ensure_pe(max_rows)
 
     def ensure_pe(self, n: int) -> torch.Tensor:
+        """Positional table with at least ``n`` rows.  A table that has been handed out is never freed:
+        CUDA graphs captured by cached Sessions keep its address, and the caching allocator would hand
+        the block to someone else."""
         if self._pe is None or self._pe.shape[0] < n:
+            if self._pe is not None:
+                self._pe_retired.append(self._pe)
             self._pe = sinusoidal_table(max(n, 1), self.d).to(self.device)
         return self._pe
+
+
+def check_ids(ids: torch.Tensor, n: int, what: str, lo: int = 0) -> None:
+    """Token ids index embedding tables and logits rows with no bounds check in the kernels; the
+    reference raises IndexError for an id outside its table (F.one_hot / nn.Embedding), so does this.
+    Host tensors are checked on the host; device tensors cost one synchronising reduction per batch
+    (never per denoise step).  VB200_CHECK_IDS=0 skips it."""
+    if ids.numel() == 0 or os.environ.get("VB200_CHECK_IDS", "1")[:1] == "0":
+        return
+    mn, mx = torch.aminmax(ids)
+    mn, mx = int(mn), int(mx)
+    if mn < lo or mx >= n:
+        raise IndexError(f"{what}: ids must lie in [{lo}, {n}), got [{mn}, {mx}]")
 
 
 class BatchLayout:
     """Packed-row layout of one batch of utterances (host-built once, constant across steps)."""
 
-    def __init__(self, text_list, proms_list, resp_lens, device, gids=None):
+    def __init__(self, text_list, proms_list, resp_lens, device, gids=None, n_text: int | None = None,
+                 n_codes: int | None = None):
         dev = torch.device(device)
         B = len(text_list)
         if B == 0:
@@ -149,6 +168,11 @@ class BatchLayout:
         self.resp_row_utt, self.resp_row_index = up(resp_row_utt), up(resp_row_index)
         text = torch.cat([t.reshape(-1) for t in text_list]).to(torch.int32)
         proms = torch.cat([p.reshape(-1, 8) for p in proms_list]).to(torch.int32)
+        self.n_text, self.n_codes = n_text, n_codes
+        if n_text is not None:
+            check_ids(text, n_text, "text_list")
+        if n_codes is not None:
+            check_ids(proms, n_codes, "proms_list")
         self.text_ids = text.contiguous().to(dev, non_blocking=True)
         self.prom_ids = proms.contiguous().to(dev, non_blocking=True)
         self.h2d_bytes = int(utt.nbytes + row_utt.nbytes + (B + 1) * 4 + resp_row_utt.nbytes +
@@ -209,6 +233,10 @@ class DenoiserEngine:
                 use_time: bool, hidden_out: list | None = None, head: bool = True) -> torch.Tensor:
         """resp_ids int32 (M_resp, levels_in); level_utt int32 (B) = AdaLN row (and time_emb row when
         use_time).  Returns ws.logits (M_resp, n_out): classifier(x) on the response rows."""
+        with torch.cuda.device(self.w.device):      # launches go to the CURRENT device's stream (lib.stream)
+            return self._forward(lay, ws, resp_ids, level_utt, use_time, hidden_out, head)
+
+    def _forward(self, lay, ws, resp_ids, level_utt, use_time, hidden_out, head):
         w = self.w
         sv = self.simt
         levels_in = int(resp_ids.shape[1])
@@ -307,6 +335,10 @@ class Session:
             raise ValueError("batch shape does not match this session")
         text = torch.cat([t.reshape(-1) for t in text_list]).to(torch.int32)
         proms = torch.cat([p.reshape(-1, 8) for p in proms_list]).to(torch.int32)
+        if lay.n_text is not None:
+            check_ids(text, lay.n_text, "text_list")
+        if lay.n_codes is not None:
+            check_ids(proms, lay.n_codes, "proms_list")
         lay.text_ids.copy_(text, non_blocking=True)
         lay.prom_ids.copy_(proms, non_blocking=True)
         moved = (text.numel() + proms.numel()) * 4
@@ -322,6 +354,10 @@ class Session:
         """for t = S-1 .. 1 (never t = 0, as the reference, ar_discrete.py:750):
         logits = denoiser(x_t, t); x_{t-1} = p_sample(logits, t, x_t), in place on self.x_t.
         uniforms_fn(t) -> float32 (M_resp*n_levels, K) supplies the reference's torch.rand (parity)."""
+        with torch.cuda.device(self.eng.w.device):
+            return self._run(table, timesteps, transition, noise, seed, uniforms_fn, use_graph, n_levels, trace)
+
+    def _run(self, table, timesteps, transition, noise, seed, uniforms_fn, use_graph, n_levels, trace):
         eng, lay, ws, x_t, t_utt = self.eng, self.lay, self.ws, self.x_t, self.t_utt
         w, dev = eng.w, eng.w.device
         K = w.n_out // n_levels
@@ -329,12 +365,12 @@ class Session:
 
         def one_step(uniforms=None):
             if eng.profile is None and not eng.simt:
-                head_in = eng.forward(lay, ws, x_t, t_utt, use_time=True, head=False)
+                head_in = eng._forward(lay, ws, x_t, t_utt, True, None, False)
                 L.head_posterior_sample(x_t, ws.logits, head_in, w.w_cls, w.b_cls, x_t, lay.resp_row_utt, t_utt,
                                         lay.utt, table, n_levels, K, transition, noise, uniforms, seed)
                 eng.launches += 0 if L.head_fused(w.d, K, noise) else 1   # the `+= 2` below counts one of them
             else:                 # per-launch timing hooks / CUDA-core validation path: separate calls
-                logits = eng.forward(lay, ws, x_t, t_utt, use_time=True)
+                logits = eng._forward(lay, ws, x_t, t_utt, True, None, True)
                 L.posterior_sample_from_logits(x_t, None, logits, w.n_out, x_t, lay.resp_row_utt, t_utt, lay.utt,
                                                table, lay.M_resp, n_levels, K, transition, noise, uniforms, seed)
             L.step_timesteps(t_utt, -1)

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "vb200_flash_attn_varlen": ([_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p], C.c_int),
     "vb200_attn_varlen_simt": ([_p, _p, _p, _i32, _i32, _i32, _i32, _f, _p], C.c_int),
     "vb200_q_sample": ([_p] * 6 + [_i32, _i32, _i32, C.c_int, _p], C.c_int),
+    "vb200_q_sample_dense": ([_p] * 6 + [_i32, _i32, _i32, _p], C.c_int),
     "vb200_posterior_sample_from_logits": (
         [_p, _p, _p, C.c_int, _i64, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, C.c_int, C.c_int, _p, _u64, _p],
         C.c_int),
@@ -89,18 +90,37 @@ def _check(rc: int, what: str) -> None:
         raise VB200Error(f"{what} failed with status {rc}: {last_error()}")
 
 
+# Devices of the tensors handed to the call being assembled.  Every wrapper below builds its argument
+# list as ``fn(ptr(a), ptr(b), ..., stream())``: Python evaluates the arguments left to right, so by the
+# time ``stream()`` runs, ``ptr`` has seen every tensor of the call.
+_call_devices: set = set()
+
+
 def ptr(t: torch.Tensor | None):
     if t is None:
         return None
-    if not t.is_cuda:
-        raise VB200Error("vb200 kernels take CUDA tensors only (no CPU fallback)")
-    if not t.is_contiguous():
-        raise VB200Error("vb200 kernels take contiguous tensors")
+    if not t.is_cuda or not t.is_contiguous():
+        _call_devices.clear()
+        raise VB200Error("vb200 kernels take CUDA tensors only (no CPU fallback)" if not t.is_cuda
+                         else "vb200 kernels take contiguous tensors")
+    _call_devices.add(t.device.index)
     return t.data_ptr()
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """The launch stream: torch's current stream ON THE DEVICE THE TENSORS LIVE ON.  The library launches on
+    the current CUDA device (kernel attributes, SM count and the stream all belong to it), so tensors on
+    another device would be dereferenced from the wrong GPU — refused here instead (callers switch with
+    ``torch.cuda.device``; the engine and the model classes do)."""
+    devs = set(_call_devices)
+    _call_devices.clear()
+    cur = torch.cuda.current_device()
+    if len(devs) > 1:
+        raise VB200Error(f"tensors of one call live on different devices: cuda:{sorted(devs)}")
+    if devs and devs != {cur}:
+        raise VB200Error(f"tensors live on cuda:{devs.pop()} but the current CUDA device is cuda:{cur}; "
+                         "wrap the call in `with torch.cuda.device(...)`")
+    return torch.cuda.current_stream(cur).cuda_stream
 
 
 def dtype_code(dt: torch.dtype) -> int:
@@ -172,6 +192,14 @@ def q_sample(x_out, x0, t_tok, mask, uniforms, table, K, transition):
     n = x0.numel()
     _check(load().vb200_q_sample(ptr(x_out), ptr(x0), ptr(t_tok), ptr(mask), ptr(uniforms), ptr(table), n, K,
                                  table.shape[0], transition, stream()), "vb200_q_sample")
+
+
+def q_sample_dense(x_out, x0, t_tok, mask, uniforms, log_qbar):
+    """q_sample against the caller's dense fp16 (S, K, K) log(Qbar_t + eps) (bit-exact for any table)."""
+    S, K, _ = log_qbar.shape
+    assert log_qbar.dtype == torch.float16
+    _check(load().vb200_q_sample_dense(ptr(x_out), ptr(x0), ptr(t_tok), ptr(mask), ptr(uniforms), ptr(log_qbar),
+                                       x0.numel(), K, S, stream()), "vb200_q_sample_dense")
 
 
 def posterior_sample_from_logits(x_out, post_out, logits, ld_logits, x_t, row_utt, t_utt, utt, table,

@@ -20,7 +20,7 @@ from torch import Tensor, nn
 from torch.distributions import Categorical
 
 from ..b200 import lib as L
-from ..b200.engine import BatchLayout, DenoiserEngine, PackedWeights
+from ..b200.engine import BatchLayout, DenoiserEngine, PackedWeights, check_ids
 
 
 class SinusodialEmbedding(nn.Module):
@@ -202,9 +202,11 @@ class Base(nn.Module):
                 logits_dtype=torch.float32):
         """Response-row logits, list of (t'', n_out) — base.py:427-443 + :491 on the packed layout."""
         eng = self.engine()
-        lay = BatchLayout(text_list, proms_list, [len(r) for r in resps_list], eng.w.device)
+        lay = BatchLayout(text_list, proms_list, [len(r) for r in resps_list], eng.w.device,
+                          n_text=eng.w.text_w.shape[0], n_codes=eng.w.K)
         ws = eng.workspace(lay, logits_dtype=logits_dtype)
         resp = torch.cat([r.reshape(len(r), -1) for r in resps_list]).to(eng.w.device, torch.int32).contiguous()
+        check_ids(resp, eng.w.K, "resps_list")
         lv = levels.to(eng.w.device, torch.int32).contiguous()
         logits = eng.forward(lay, ws, resp, lv, use_time=use_time)
         return lay.split_resp(logits)

@@ -3,10 +3,15 @@
 The reference keeps three dense (S, K, K) fp16 tensors (``ar_discrete.py:257-277``: one-step
 matrices, their fp16 chain product ``q_mats`` and the transposes, 3 x 210 MB at S=100, K=1025) and
 indexes them with one-hot matmuls.  Both transition families have rank-structured matrices, so the
-kernels only need a few scalars per timestep.  To keep those scalars *bit-identical* to what the
-reference holds (the fp16 chain product drifts from the analytic value — row sums reach 1.002 —
-and ``eps=1e-6`` makes that drift observable), they are read out of the same fp16 chain product,
+kernels only need a few scalars per timestep.  To keep those scalars equal to what the reference
+holds (the fp16 chain product drifts from the analytic value — row sums reach 1.002 — and
+``eps=1e-6`` makes that drift observable), they are read out of the same fp16 chain product,
 computed here once with a running (K, K) matrix instead of being re-derived from alpha-bar.
+Absorbing: every entry of the product has at most two non-zero terms, so the product is exactly
+rank-structured and the scalars are bit-identical to the dense entries.  Uniform: K-term sums, so
+the dense product carries up to 2 diagonal / 3 off-diagonal values per t that differ by one fp16
+ulp; the scalars are representative entries (``tests/test_host_cpu.py`` bounds the gap), and the
+bit-exact parity path reads the dense table instead (``dense_log_qbar``).
 """
 from __future__ import annotations
 
@@ -66,6 +71,24 @@ def scalar_table(timesteps: int, K: int, transition: str) -> torch.Tensor:
         # q_sample logits are formed in fp16: log(fp16(q) + eps) (ar_discrete.py:482)
         tab[t, L.TAB_LOG_KEEP:L.TAB_LOG_BOTH + 1] = torch.log(picks + EPS).float()
     return tab
+
+
+@functools.lru_cache(maxsize=2)
+def dense_log_qbar(timesteps: int, K: int, transition: str) -> torch.Tensor:
+    """fp16 (S, K, K) ``log(Qbar_t + eps)`` — the logits ``q_sample`` forms (ar_discrete.py:482) from
+    the fp16 chain product (:270-275), for ``vb200_q_sample_dense``.  Only the *uniform* transition
+    needs it, and only for bit-exact parity runs with supplied uniforms: its K-term fp16 sums are not
+    rank-structured to the last bit (up to 2 diagonal and 3 off-diagonal values per t, placed by the
+    summation order of the GEMM), so `scalar_table` holds representative values there, exact ones
+    for absorbing (<= 2 non-zero terms per entry)."""
+    betas = cosine_beta_schedule(timesteps + 1).to(torch.float16)
+    out = torch.empty(timesteps, K, K, dtype=torch.float16)
+    cum = None
+    for t in range(timesteps):
+        one = _onestep(betas[t], K, transition)
+        cum = one if cum is None else torch.tensordot(cum, one, dims=[[1], [0]])
+        out[t] = torch.log(cum + EPS)
+    return out
 
 
 def betas_fp16(timesteps: int) -> torch.Tensor:

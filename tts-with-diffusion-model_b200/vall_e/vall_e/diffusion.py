@@ -17,7 +17,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from ..b200 import lib as L
-from ..b200.engine import BatchLayout
+from ..b200.engine import BatchLayout, check_ids
 from . import d3pm
 from .base import Base
 
@@ -46,6 +46,13 @@ class D3PMOps:
             cache[key] = d3pm.scalar_table(self.timesteps, self.num_classes, self.transition).to(device)
         return cache[key]
 
+    def _dense_log_qbar(self, device) -> Tensor:
+        cache = self.__dict__.setdefault("_tables", {})
+        key = ("dense", str(device), self.timesteps, self.num_classes, self.transition)
+        if key not in cache:
+            cache[key] = d3pm.dense_log_qbar(self.timesteps, self.num_classes, self.transition).to(device)
+        return cache[key]
+
     def __getstate__(self):
         state = super().__getstate__()
         state.pop("_tables", None)
@@ -61,11 +68,16 @@ class D3PMOps:
         if noise is None:
             noise = torch.rand(size=x_start.shape + (K,)).to(dev)
         x0 = x_start.to(torch.int32).contiguous().view(-1)
+        check_ids(x0, K, "q_sample: x_start")
         t_tok = t.to(dev, torch.int32).view(B, 1).expand(B, W).contiguous().view(-1)
         m = mask.to(dev, torch.int32).expand(B, W).contiguous().view(-1)
         out = torch.empty_like(x0)
-        L.q_sample(out, x0, t_tok, m, noise.to(dev, torch.float32).contiguous(), self._table(dev), K,
-                   _TRANSITIONS[self.transition])
+        u = noise.to(dev, torch.float32).contiguous()
+        with torch.cuda.device(dev):
+            if self.transition == "uniform":  # bit-exact needs the dense fp16 chain product (d3pm.dense_log_qbar)
+                L.q_sample_dense(out, x0, t_tok, m, u, self._dense_log_qbar(dev))
+            else:
+                L.q_sample(out, x0, t_tok, m, u, self._table(dev), K, _TRANSITIONS[self.transition])
         return out.view(B, W).long()
 
     # ------------------------------------------------------------------ reverse step (row P)
@@ -79,6 +91,7 @@ class D3PMOps:
         if logits.dtype not in (torch.float32, torch.float16, torch.bfloat16):
             logits = logits.float()
         x_t = x.to(torch.int32).contiguous().view(-1)
+        check_ids(x_t, K, "p_sample: x")
         row_utt = torch.arange(B, device=dev, dtype=torch.int32).repeat_interleave(W)
         t_utt = t.to(dev, torch.int32).contiguous()
         utt = torch.zeros(B, L.U_STRIDE, dtype=torch.int32, device=dev)
@@ -87,8 +100,9 @@ class D3PMOps:
         out = torch.empty_like(x_t)
         post = torch.empty(B * W, K, dtype=torch.float32, device=dev) if want_post else None
         uni = noise.to(dev, torch.float32).contiguous() if noise is not None else None
-        L.posterior_sample_from_logits(out, post, logits, K, x_t, row_utt, t_utt, utt, self._table(dev),
-                                       B * W, 1, K, _TRANSITIONS[self.transition], noise_mode, uni, seed)
+        with torch.cuda.device(dev):
+            L.posterior_sample_from_logits(out, post, logits, K, x_t, row_utt, t_utt, utt, self._table(dev),
+                                           B * W, 1, K, _TRANSITIONS[self.transition], noise_mode, uni, seed)
         return out.view(B, W).long(), (post.view(B, W, K) if want_post else None)
 
     def q_posterior_logits(self, x_start: Tensor, x_t: Tensor, t: Tensor, x_start_logits: bool = True) -> Tensor:
@@ -190,20 +204,27 @@ class Diffusion(D3PMOps, Base):
         ses = self._session(text_list, proms_list, resp_lens, gids)
         lay, x_t = ses.lay, ses.x_t
         if resps_list is not None:
-            x_t.copy_(torch.cat([r.reshape(len(r), self.n_levels) for r in resps_list]).to(torch.int32),
-                      non_blocking=True)
+            x_T = torch.cat([r.reshape(len(r), self.n_levels) for r in resps_list]).to(torch.int32)
+            check_ids(x_T, self.num_classes, "resps_list (x_T)")
+            x_t.copy_(x_T, non_blocking=True)
         elif self.transition == "absorbing":
             x_t.fill_(self.mask_id)
         else:
-            g = torch.Generator().manual_seed(seed)
-            x_t.copy_(torch.randint(0, self.num_classes, (lay.M_resp, self.n_levels), generator=g,
-                                    dtype=torch.int32), non_blocking=True)
+            # uniform start state, one stream per utterance keyed by (seed, GLOBAL utterance id) like the Philox
+            # step noise: an utterance's x_T does not depend on which rank or batch it landed in
+            ids = gids if gids is not None else range(lay.B)
+            parts = []
+            for gid, n in zip(ids, lay.t_resp):
+                g = torch.Generator().manual_seed((int(seed) * 0x9E3779B1 + int(gid) * 0x85EBCA77 + 0x5D3B) % (1 << 63))
+                parts.append(torch.randint(0, self.num_classes, (n, self.n_levels), generator=g, dtype=torch.int32))
+            x_t.copy_(torch.cat(parts), non_blocking=True)
         noise = L.NOISE_GREEDY if greedy else (L.NOISE_UNIFORMS if uniforms_fn is not None else L.NOISE_PHILOX)
         ses.run(self._table(dev), self.timesteps, _TRANSITIONS[self.transition], noise=noise, seed=seed,
                 uniforms_fn=uniforms_fn, use_graph=use_graph, n_levels=self.n_levels, trace=trace)
         if as_bqt:        # one (B, 8, T_max) int64 tensor in the EnCodec decoder's layout + the frame counts
             bqt = torch.empty(lay.B, self.n_levels, max(lay.t_resp), dtype=torch.int64, device=dev)
-            L.codes_to_bqt(bqt, x_t, lay.utt, pad=0)
+            with torch.cuda.device(dev):
+                L.codes_to_bqt(bqt, x_t, lay.utt, pad=0)
             return (bqt.cpu() if to_host else bqt), list(lay.t_resp)
         out = x_t.to("cpu", non_blocking=False) if to_host else x_t
         return [r.long() for r in out.split(lay.t_resp, dim=0)]
@@ -231,14 +252,16 @@ class Diffusion(D3PMOps, Base):
         else:
             tt = torch.as_tensor(t, dtype=torch.int32, device=dev)
             sweep = [tt.expand(lay.B).contiguous() if tt.dim() == 0 else tt.contiguous()]
+        check_ids(x0, self.num_classes, "resps_list (x_0)")
         x_t = torch.empty_like(x0)
         loss = torch.empty(lay.M_resp, self.n_levels, dtype=torch.float32, device=dev)
         total = torch.zeros((), dtype=torch.float32, device=dev)
         for i, t_utt in enumerate(sweep):
             t_tok = t_utt[lay.resp_row_utt.long()].repeat_interleave(self.n_levels).contiguous()
-            L.q_sample_philox(x_t.view(-1), x0.view(-1), t_tok, None, table, self.num_classes, tr, seed=seed + i)
-            head_in = eng.forward(lay, ws, x_t, t_utt, use_time=True, head=False)
-            L.head_ce_loss(loss, head_in, eng.w.w_cls, eng.w.b_cls, x0, self.n_levels, self.num_classes)
+            with torch.cuda.device(dev):
+                L.q_sample_philox(x_t.view(-1), x0.view(-1), t_tok, None, table, self.num_classes, tr, seed=seed + i)
+                head_in = eng.forward(lay, ws, x_t, t_utt, use_time=True, head=False)
+                L.head_ce_loss(loss, head_in, eng.w.w_cls, eng.w.b_cls, x0, self.n_levels, self.num_classes)
             total += loss.mean()
         total /= len(sweep)
         return (total, loss, x_t) if return_per_token else total
@@ -253,7 +276,8 @@ class Diffusion(D3PMOps, Base):
         if ses is None:
             if len(cache) >= 4:
                 cache.pop(next(iter(cache)))
-            lay = BatchLayout(text_list, proms_list, resp_lens, eng.w.device, gids=gids)
+            lay = BatchLayout(text_list, proms_list, resp_lens, eng.w.device, gids=gids,
+                              n_text=eng.w.text_w.shape[0], n_codes=eng.w.K)
             ses = cache[sig] = eng.session(lay)
             self.last_h2d_bytes = lay.h2d_bytes
         else:
