@@ -483,8 +483,12 @@ def test_wrong_ids_are_refused_before_any_launch():
     bad[0][2, 3] = K
     with pytest.raises(IndexError):
         m.generate_audio([x.to(DEV) for x in text], [x.to(DEV) for x in proms], [x.to(DEV) for x in bad])
+    neg = proms[0].clone()
+    neg[1, 2] = -1
     with pytest.raises(IndexError):
-        m.generate_audio([x.to(DEV) for x in text], [(proms[0] - 1).to(DEV)], resp_lens=[9])
+        m.generate_audio([x.to(DEV) for x in text], [neg.to(DEV)], resp_lens=[9])
+    with pytest.raises(IndexError):
+        m.generate_audio([torch.full_like(text[0], K).to(DEV)], [x.to(DEV) for x in proms], resp_lens=[9])
     with pytest.raises(IndexError):
         m.p_sample(torch.zeros(1, 2, K, device=DEV), torch.tensor([1]), torch.tensor([[0, K]], device=DEV), greedy=True)
 
