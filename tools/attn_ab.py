@@ -37,9 +37,9 @@ for lens, amp in (([256, 255, 385, 16, 17], 1.0), ([1027, 1027], 1.0), ([2527], 
     torch.cuda.synchronize()
     err = (out.float() - ref.float()).abs().max().item()
     print(f"  check lens={lens} amp={amp}: max abs err {err:.2e}", "OK" if err < 2.5e-2 * amp else "FAIL")
-for lens in ([1027] * 256, [2527] * 8, [1024] * 64):
-    ms, tf, *_ = run(lens)
-    print(f"  B={len(lens)} T={lens[0]}: {ms:.3f} ms {tf:.0f} TFLOP/s", flush=True)
+for lens in ([1027] * 256, [2527] * 8, [1024] * 64, [1027]):
+    best = min(run(lens, iters=20 if len(lens) > 1 else 200)[:2] for _ in range(3))     # best of 3: boxes differ in clocks
+    print(f"  B={len(lens)} T={lens[0]}: {best[0]:.4f} ms {best[1]:.0f} TFLOP/s", flush=True)
 ''' % str(ROOT / "tts-with-diffusion-model_b200")
 
 libs = [VAR / f"lib{n}.so" for n in sys.argv[1:]] or sorted(VAR.glob("lib*.so"))

@@ -13,3 +13,6 @@ for spec in "$@"; do
        build/obj/gemm_tcgen05.o build/obj/head_sample_tcgen05.o build/obj/debug_simt.o build/variants/attn_$name.o -gencode arch=compute_100a,code=sm_100a
   echo "built build/variants/lib$name.so ($defs)"
 done
+
+# Timeline build for tools/attn_trace.py:  tools/attn_variants.sh trace:"-DVB200_ATTN_TRACE"  then
+#   VB200_LIB=tts-with-diffusion-model_b200/build/variants/libtrace.so python tools/attn_trace.py 64 1024

@@ -143,6 +143,19 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x, float& p0, float& p1) {
 #endif
 namespace attn { constexpr int EXP_CHUNK = VB200_ATTN_EXP_CHUNK; }
 
+#ifdef VB200_ATTN_TRACE
+// Debug build only (tools/attn_trace.py): per-CTA clock64() stamps of the softmax warp 0 and the MMA warp.
+constexpr int TRACE_CTAS = 1024, TRACE_BLOCKS = 16, TRACE_EVENTS = 8;
+__device__ unsigned long long g_attn_trace[TRACE_CTAS * 2 * TRACE_BLOCKS * TRACE_EVENTS];
+#define VB_TR(slot, j, ev)                                                                               \
+  do {                                                                                                   \
+    if (lane == 0 && cta_lin < TRACE_CTAS && (j) < TRACE_BLOCKS)                                         \
+      g_attn_trace[((cta_lin * 2 + (slot)) * TRACE_BLOCKS + (j)) * TRACE_EVENTS + (ev)] = clock64();     \
+  } while (0)
+#else
+#define VB_TR(slot, j, ev) do {} while (0)
+#endif
+
 __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
     const __grid_constant__ CUtensorMap tm_qkv, __nv_bfloat16* __restrict__ out,
     const int32_t* __restrict__ cu_rows, int n_heads, float scale_log2, float opaque_zero) {
@@ -177,6 +190,15 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
   const int lane = threadIdx.x & 31;
+#ifdef VB200_ATTN_TRACE
+  const int cta_lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  if (threadIdx.x == 0 && cta_lin < TRACE_CTAS) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_attn_trace[((cta_lin * 2 + 1) * TRACE_BLOCKS + TRACE_BLOCKS - 1) * TRACE_EVENTS + 7] = smid;
+    g_attn_trace[((cta_lin * 2 + 1) * TRACE_BLOCKS + TRACE_BLOCKS - 1) * TRACE_EVENTS + 6] = clock64();
+  }
+#endif
 
   if (threadIdx.x == SOFTMAX_WARPS * 32) {        // first lane of the TMA warp
     tma_prefetch_desc(&tm_qkv);
@@ -285,11 +307,13 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
         mbar_wait(&k_full[(j + 1) % KV_STAGES], ((j + 1) / KV_STAGES) & 1);
         mbar_wait(s_free, j & 1);                            // S(j) is in the softmax warps' registers
         tc_fence_after();
+        VB_TR(1, j, 0);
         issue_s(j + 1);
       }
       mbar_wait(&v_full[j % KV_STAGES], (j / KV_STAGES) & 1);
       mbar_wait(p_full, j & 1);                              // P(j) written
       tc_fence_after();
+      VB_TR(1, j, 1);
       issue_pv(j);
     }
   } else {
@@ -315,11 +339,14 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
       const uint64_t zero2 = pack2(opaque_zero, opaque_zero);
       for (int j = 0; j < nblk; ++j) {
         const bool tail = (j == nblk - 1) && last_valid < BKV;
+        if (warp == 0) VB_TR(0, j, 0);
         mbar_wait(s_full, j & 1);
         tc_fence_after();
+        if (warp == 0) VB_TR(0, j, 1);
         uint32_t s[64];
         tmem_ld_16x2_x64(t_x + COL_S, s);
         tmem_ld_wait();
+        if (warp == 0) VB_TR(0, j, 2);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(s_free);              // S(j+1) may overwrite the buffer
@@ -360,6 +387,9 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
           }
         }
         const float mneg = -m_ref * scale_log2;
+#ifdef VB200_ATTN_TRACE
+        if (warp == 0 && mneg != 12345.f) VB_TR(0, j, 3);     // after the row maximum (data dependent: stays in place)
+#endif
         const uint64_t scale2 = pack2(scale_log2, scale_log2), mneg2 = pack2(mneg, mneg);
         // The 32 score pairs go in chunks of EXP_CHUNK pairs, and chunk k's offset is made to DEPEND on the
         // sum of chunk k-2 (an FFMA2 with a zero the compiler cannot see through).  Without it ptxas hoists
@@ -392,15 +422,20 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
         unpack2(ps[0], a0, a1);
         unpack2(ps[1], a2, a3);
         l += (a0 + a1) + (a2 + a3);
+#ifdef VB200_ATTN_TRACE
+        if (warp == 0 && l != -1.f) VB_TR(0, j, 4);            // after the exp pass
+#endif
         if (j > 0) {
           mbar_wait(pv_done, (j - 1) & 1);               // P V(j-1) has consumed the P buffer
           tc_fence_after();
         }
+        if (warp == 0) VB_TR(0, j, 5);
         tmem_st_16x2_x32(t_x + COL_P, s);
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);              // one arrival per warp
+        if (warp == 0) VB_TR(0, j, 6);
       }
       // O / l -> bf16: this thread's half (32 of the 64 dims) of its row
       mbar_wait(pv_done, (nblk - 1) & 1);
@@ -438,6 +473,14 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
 }  // namespace vb200
 
 using namespace vb200;
+
+#ifdef VB200_ATTN_TRACE
+extern "C" int vb200_debug_attn_trace(unsigned long long* host_dst, size_t n_words) {
+  const size_t n = sizeof(g_attn_trace) / sizeof(unsigned long long);
+  cudaError_t e = cudaMemcpyFromSymbol(host_dst, g_attn_trace, (n_words < n ? n_words : n) * sizeof(unsigned long long));
+  return e == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, const int32_t* cu_rows,
                                        int32_t B, int32_t max_T, int32_t M, int32_t n_heads,
