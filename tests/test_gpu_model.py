@@ -480,7 +480,7 @@ def test_wrong_ids_are_refused_before_any_launch():
     m, _ = _make(K, d, h, nl, S, "absorbing", seed=8)
     text, proms, xt = _batch(K, [(3, 5, 9)], 2)
     bad = [xt[0].clone()]
-    bad[0][2, 3] = K
+    bad[0][2, 3] = m.num_classes           # K itself is the absorbing mask id, a legal x_T entry
     with pytest.raises(IndexError):
         m.generate_audio([x.to(DEV) for x in text], [x.to(DEV) for x in proms], [x.to(DEV) for x in bad])
     neg = proms[0].clone()
@@ -490,7 +490,8 @@ def test_wrong_ids_are_refused_before_any_launch():
     with pytest.raises(IndexError):
         m.generate_audio([torch.full_like(text[0], K).to(DEV)], [x.to(DEV) for x in proms], resp_lens=[9])
     with pytest.raises(IndexError):
-        m.p_sample(torch.zeros(1, 2, K, device=DEV), torch.tensor([1]), torch.tensor([[0, K]], device=DEV), greedy=True)
+        m.p_sample(torch.zeros(1, 2, m.num_classes, device=DEV), torch.tensor([1]),
+                   torch.tensor([[0, m.num_classes]], device=DEV), greedy=True)
 
 
 def test_uniform_start_state_is_keyed_by_global_utterance_id():

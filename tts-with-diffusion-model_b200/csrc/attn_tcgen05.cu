@@ -29,6 +29,7 @@
 // the packed-row layout — and the last key block only issues the MMAs (N resp. K rounded up to 16) its
 // valid keys need.
 #include "common.cuh"
+#include <type_traits>
 
 namespace vb200 {
 
@@ -91,6 +92,13 @@ __device__ __forceinline__ void tmem_st_16x2_x16(uint32_t taddr, const uint32_t 
       "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// 16 lanes x 16 columns from 8 registers: t < 16 -> columns [c, c+8), t >= 16 -> [c+8, c+16)
+__device__ __forceinline__ void tmem_st_16x2_x8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x32bx2.x8.b32 [%0], 8, {%1,%2,%3,%4,%5,%6,%7,%8};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
       : "memory");
 }
 // 16 lanes x 64 columns: t < 16 -> columns [c, c+32), t >= 16 -> [c+32, c+64)
@@ -337,8 +345,36 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
     } else {
       float m_ref = -INFINITY, l = 0.f;                  // reference maximum of the row; this half's share of the row sum
       const uint64_t zero2 = pack2(opaque_zero, opaque_zero);
-      for (int j = 0; j < nblk; ++j) {
-        const bool tail = (j == nblk - 1) && last_valid < BKV;
+      // The reference maximum moves when a block exceeds it by 2^8: rescales this warp's rows of O (TMEM) and l.
+      auto move_reference = [&](float bm, int j) {
+        if (j == 0) {
+          m_ref = bm;                                      // block 0 holds at least one valid key
+          return;
+        }
+        const bool grow = (bm - m_ref) * scale_log2 > RESCALE_LOG2;
+        if (__any_sync(0xffffffffu, grow)) {
+          // rare after the first block
+          const float m_new = grow ? bm : m_ref;
+          const float alpha = ex2_approx((m_ref - m_new) * scale_log2);      // 1 for rows that stay
+          m_ref = m_new;
+          l *= alpha;
+          mbar_wait(pv_done, (j - 1) & 1);                 // O complete up to block j-1, P V(j) not issued yet
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[16];
+            tmem_ld_16x2_x16(t_x + COL_O + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_16x2_x16(t_x + COL_O + c * 32, o);
+          }
+        }
+      };
+      // One 128-key block.  TAIL (compile time): keys >= last_valid are masked.  The full blocks run in
+      // their own loop so that their code carries nothing of the ragged end.
+      auto key_block = [&](int j, auto tail_tag) {
+        constexpr bool tail = decltype(tail_tag)::value;
         if (warp == 0) VB_TR(0, j, 0);
         mbar_wait(s_full, j & 1);
         tc_fence_after();
@@ -363,29 +399,7 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
         }
         float bm = fmaxf(fmaxf(bm0, bm1), fmaxf(bm2, bm3));
         bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));       // the row's other half
-        if (j == 0) {
-          m_ref = bm;                                    // block 0 holds at least one valid key
-        } else {
-          const bool grow = (bm - m_ref) * scale_log2 > RESCALE_LOG2;
-          if (__any_sync(0xffffffffu, grow)) {
-            // rare after the first block: move the reference and rescale this warp's rows of O and l
-            const float m_new = grow ? bm : m_ref;
-            const float alpha = ex2_approx((m_ref - m_new) * scale_log2);      // 1 for rows that stay
-            m_ref = m_new;
-            l *= alpha;
-            mbar_wait(pv_done, (j - 1) & 1);             // O complete up to block j-1, P V(j) not issued yet
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-              uint32_t o[16];
-              tmem_ld_16x2_x16(t_x + COL_O + c * 32, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-              tmem_st_16x2_x16(t_x + COL_O + c * 32, o);
-            }
-          }
-        }
+        move_reference(bm, j);
         const float mneg = -m_ref * scale_log2;
 #ifdef VB200_ATTN_TRACE
         if (warp == 0 && mneg != 12345.f) VB_TR(0, j, 3);     // after the row maximum (data dependent: stays in place)
@@ -436,6 +450,51 @@ __global__ void __launch_bounds__(attn::THREADS, 2) flash_attn_kernel(
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);              // one arrival per warp
         if (warp == 0) VB_TR(0, j, 6);
+      };
+      // Last block of at most 32 keys (an utterance of T = 1027 rows ends in 3): one 32-column chunk, lane
+      // t < 16 holds keys 0..15 of its row, lane t + 16 keys 16..31, instead of a masked 128-key pass.
+      auto short_block = [&](int j) {
+        mbar_wait(s_full, j & 1);
+        tc_fence_after();
+        uint32_t sq[16];
+        tmem_ld_16x2_x16(t_x + COL_S, sq);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        float bm = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (t1 * 16 + i >= last_valid) sq[i] = __float_as_uint(-INFINITY);
+          bm = fmaxf(bm, __uint_as_float(sq[i]));
+        }
+        bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 16));
+        move_reference(bm, j);
+        const float mneg = -m_ref * scale_log2;
+        uint32_t pq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sq[2 * i]), scale_log2, mneg));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sq[2 * i + 1]), scale_log2, mneg));
+          l += p0 + p1;
+          pq[i] = pack_bf16x2(p0, p1);
+        }
+        if (j > 0) {
+          mbar_wait(pv_done, (j - 1) & 1);
+          tc_fence_after();
+        }
+        tmem_st_16x2_x8(t_x + COL_P, pq);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      };
+      const int n_full = last_valid < BKV ? nblk - 1 : nblk;
+#pragma unroll 1
+      for (int j = 0; j < n_full; ++j) key_block(j, std::false_type{});
+      if (n_full < nblk) {
+        if (last_valid <= 32) short_block(n_full);
+        else key_block(n_full, std::true_type{});
       }
       // O / l -> bf16: this thread's half (32 of the 64 dims) of its row
       mbar_wait(pv_done, (nblk - 1) & 1);
