@@ -121,6 +121,25 @@ def test_attention(L, variant, lens, heads):
     assert err < 2e-2, err
 
 
+@pytest.mark.parametrize("amp", [1.0, 5.0])
+def test_attention_last_block_lengths(L, amp):
+    """Every shape of the ragged end: a last key block of 1 .. 32 keys takes the one-chunk path (also as the
+    ONLY block, T <= 32), 33 .. 127 the masked 128-key pass, 128 none; with amp = 5 the scores spread over
+    ~2^60, so the row maximum moves in late blocks too (rescale of O in TMEM from the short block)."""
+    lens = [1, 15, 16, 17, 31, 32, 33, 128 + 1, 128 + 16, 128 + 17, 128 + 32, 128 + 33, 256 + 3, 128 + 95, 128 + 127, 384]
+    heads = 2
+    M, d = sum(lens), heads * 64
+    qkv = (_rand_bf16((M, 3 * d), 11).float() * amp).bfloat16()
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=DEV)
+    out = torch.full((M, d), float("nan"), dtype=torch.bfloat16, device=DEV)
+    L.flash_attn_varlen(out, qkv, cu, max(lens), heads, 64 ** -0.5)
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, lens, heads)
+    err = (out.float() - ref).abs()
+    assert torch.isfinite(out.float()).all()
+    assert err.max().item() < (2e-2 if amp == 1.0 else 3e-2 * amp), err.max().item()      # bf16 output ulp grows with |V|
+
+
 # ---------------------------------------------------------------- elementwise
 def test_adaln_layernorm_gather(L):
     from oracle import denoiser as on
