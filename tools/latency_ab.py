@@ -10,7 +10,7 @@ sys.path.insert(0, str(ROOT / "tts-with-diffusion-model_b200"))
 sys.path.insert(0, str(ROOT))
 from vall_e.b200 import lib as L  # noqa: E402
 from vall_e.vall_e.diffusion import Diffusion  # noqa: E402
-from bench import MODEL, synth_batch  # noqa: E402
+from bench import MODEL, synth_utterance  # noqa: E402
 
 L.load()
 dev = torch.device("cuda")
@@ -21,8 +21,8 @@ for blk in model.blocks:
     for sub in (blk.attn, blk.ffn):
         torch.nn.init.normal_(sub.norm.emb.weight, std=0.02)
 model = model.to(dev)
-text, proms = synth_batch(1, 50, 225, seed=7)
-text, proms = [t.to(dev) for t in text], [p.to(dev) for p in proms]
+u = synth_utterance(7, 50, 225)
+text, proms = [u[0].to(dev)], [u[1].to(dev)]
 codes = model.generate_audio(text, proms, resp_lens=[750], seed=3)
 chk = int((codes[0].double() * torch.arange(1, 6001, device=dev).view(750, 8)).sum().item())
 ses = model._session(text, proms, [750], [0])

@@ -17,6 +17,9 @@
 
 #include "common.cuh"
 
+#ifndef VB200_GEMM_BIAS_PREFETCH
+#define VB200_GEMM_BIAS_PREFETCH 1
+#endif
 #ifndef VB200_GEMM_EARLY_LOAD
 #define VB200_GEMM_EARLY_LOAD 1
 #endif
@@ -237,6 +240,12 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
       const int m_blk = tile / num_n, n_blk = tile % num_n;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      if (EPI != VB200_EPI_NONE && VB200_GEMM_BIAS_PREFETCH) {
+        // this warp's slice of the bias into L1 while the accumulator is still being computed: in a one-tile
+        // launch (one utterance) the first __ldg below is otherwise an exposed L2 round trip per GEMM
+        const int nb0 = n_blk * BN + half * HALF_COLS + lane * 32;
+        if (lane * 32 < HALF_COLS && nb0 < N) prefetch_l1(bias + nb0);
+      }
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const int row0 = (m_blk * CTAS + cta_rank) * BM + quad * 32;
