@@ -133,14 +133,16 @@ int cached_tmap(CUtensorMap* out, vb200_dtype dtype, const void* ptr, uint64_t i
 }  // namespace vb200
 
 namespace vb200 {
-bool pdl_enabled() {
+thread_local int g_pdl_tag = 0;
+int pdl_mask() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VB200_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;
+    v = e ? atoi(e) : (4 | 8 | 32);      // default: the one-CTA-per-SM tensor-core kernels (see common.cuh)
   }
-  return v == 1;
+  return v;
 }
+bool pdl_enabled() { return (pdl_mask() & 1) != 0; }
 }  // namespace vb200
 
 extern "C" const char* vb200_last_error(void) { return vb200::g_err; }

@@ -568,6 +568,7 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
       carveout_done.fetch_or(bit, std::memory_order_release);
     }
   }
+  PdlTag pdl_tag(16);
   VB_CHECK_CUDA(launch_pdl(flash_attn_kernel, grid, dim3(THREADS), SMEM_BYTES, static_cast<cudaStream_t>(stream), 1,
                            tm, static_cast<__nv_bfloat16*>(out_bf16), cu_rows, n_heads, sl2, 0.0f));
   VB_CHECK_CUDA(cudaGetLastError());

@@ -39,18 +39,24 @@ int head_sample_fused(int32_t* x_out, const void* head_in, const void* W, const 
 int head_ce_fused(float* loss_out, const void* head_in, const void* W, const float* bias, const int32_t* targets,
                   int n_rows, int d, int n_levels, int K, int in_f16, cudaStream_t st);
 
-// Programmatic dependent launch (PDL), opt-in with VB200_PDL=1.  Every kernel of the denoise step
-// goes through launch_pdl() and brackets its first access to memory that an earlier kernel
-// produced (or still reads) with pdl_wait(), so that with the "programmatic stream serialization"
-// attribute its CTAs may become resident and run their prologue (barrier init, TMEM allocation,
-// tensor-map prefetch, reads of STATIC data such as weights or the batch layout) while the previous
-// kernel drains.  Valid under stream capture too.  Measured on B200 at batch 1 (89 kernels per
-// denoise step, graph replay): 0.878 ms with it, 0.861 ms without — the kernels of one step each
-// fill most SMs with CTAs of equal length, so there is no tail to overlap — hence off by default.
-// Re-measured with the final kernels: 832 us with it against 797 us without, and the same 832 us when the
-// GEMM / attention kernels trigger late (producer warp, after its last load) instead of at the top, so
-// it is not later kernels piling up on the SMs: replaying a graph with programmatic edges is simply
-// ~0.4 us per kernel slower here than plain stream order.
+// Programmatic dependent launch (PDL).  Every kernel of the denoise step goes through launch_pdl() and
+// brackets its first access to memory that an earlier kernel produced (or still reads) with pdl_wait(), so
+// that with the "programmatic stream serialization" attribute its CTAs may become resident and run their
+// prologue (barrier init, TMEM allocation, tensor-map prefetch, TMA loads of STATIC data: the first ring of
+// weight tiles) while the previous kernel drains.  Valid under stream capture too.
+// Which launches carry the attribute is a bit mask (VB200_PDL, default 4 | 8 | 32), measured per class on the
+// batch-1 denoise step (88 kernels, one graph replay; tools/latency_ab.py, same box):
+//   4 | 8  GEMMs (QKV / FFN1 behind an AdaLN, the residual GEMMs behind attention / FFN1)   765 -> 735 us,
+//          -> 722 us once the weight halves of the first ring are requested before the wait
+//   32     fused classifier + reverse step                                                   -1.5 us
+//   2      AdaLN                                                                             +17 us
+//   16     attention                                                                         +46 us
+//   1      every launch (what rounds 1 and 2 first measured: 832 against 797 us, "PDL is slower")
+// The difference is CTA placement: an early-launched grid takes SM slots as they free up.  The tensor-core
+// GEMMs fit one CTA per SM, so nothing changes for them but the start time; attention (two CTAs per SM) and
+// AdaLN (eight blocks) get PACKED onto the first SMs that drain instead of being spread breadth-first over
+// idle SMs, and a one-wave launch then runs at half speed.  At 32 utterances per GPU the same mask gives
+// 12.56 -> 12.50 ms per step; at 256 it is neutral.
 // cudaFuncSetAttribute is per DEVICE: each launch site remembers which devices it has configured (a
 // process that drives several GPUs would otherwise launch with the 48 KB default on the second one).
 #define VB_CONFIGURE_SMEM(kern, bytes)                                                                   \
@@ -65,6 +71,15 @@ int head_ce_fused(float* loss_out, const void* head_in, const void* W, const flo
     }                                                                                                    \
   } while (0)
 bool pdl_enabled();
+// VB200_PDL is a bit mask: 1 = every launch; 2 = AdaLN; 4 = GEMMs behind an AdaLN (QKV, FFN1); 8 = residual GEMMs;
+// 16 = attention; 32 = fused classifier + reverse step.  A launch site names its class through PdlTag before calling launch_pdl().
+int pdl_mask();
+extern thread_local int g_pdl_tag;
+struct PdlTag {
+  int prev;
+  explicit PdlTag(int t) : prev(g_pdl_tag) { g_pdl_tag = t; }
+  ~PdlTag() { g_pdl_tag = prev; }
+};
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               int cluster_x, Args&&... args) {
@@ -82,7 +97,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     attr[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (pdl_enabled()) {
+  if (pdl_mask() & (1 | g_pdl_tag)) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

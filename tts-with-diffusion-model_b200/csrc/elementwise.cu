@@ -363,6 +363,7 @@ extern "C" int vb200_adaln(void* out_bf16, vb200_dtype out_dtype, const float* x
   if (d % 256 == 0 && d <= 1024) {
     // contiguous row ranges per warp; enough warps for ~4 resident blocks per SM.  Small M (one
     // utterance at a time) gets one row per warp: there the kernel is latency-, not bandwidth-bound.
+    PdlTag pdl_tag(2);
     const int total_warps = num_sms() * 4 * 8;
     const int rpw = (M + total_warps - 1) / total_warps;
     const int warps = (M + rpw - 1) / rpw;

@@ -120,16 +120,18 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     // the block-wide sync below (TMEM allocation): the first TMA round trip is on the critical path
     // of the one-wave launches of a single utterance
     if (CTAS == 1 && tile0 < num_tiles) {
+      // With programmatic dependent launch (VB200_PDL & 4 / 8) this CTA may be resident while the previous
+      // kernel still runs: the WEIGHT halves of the first ring (static data) go out at once, the activation
+      // halves once the previous kernel has completed.
       pdl_launch_dependents();
-      pdl_wait();                                   // A is an earlier kernel's output
       const int m_row = (tile0 / num_n) * BM, n_row = (tile0 % num_n) * BN;
       const int n_pre = num_kb < STAGES ? num_kb : STAGES;
       for (int kb = 0; kb < n_pre; ++kb) {
-        uint8_t* sa = smem + kb * STAGE_BYTES;
         mbar_arrive_expect_tx(&full[kb], STAGE_BYTES);
-        tma_load_2d(sa, &tm_a, &full[kb], kb * BK, m_row);
-        tma_load_2d(sa + A_BYTES, &tm_b, &full[kb], kb * BK, n_row);
+        tma_load_2d(smem + kb * STAGE_BYTES + A_BYTES, &tm_b, &full[kb], kb * BK, n_row);
       }
+      pdl_wait();                                   // A is an earlier kernel's output
+      for (int kb = 0; kb < n_pre; ++kb) tma_load_2d(smem + kb * STAGE_BYTES, &tm_a, &full[kb], kb * BK, m_row);
     }
 #endif
   }
@@ -335,6 +337,7 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, vb200_dtype a_d
                        int M, int N, int K, cudaStream_t st) {
   const uint32_t a_f16 = a_dt == VB200_F16 ? 1u : 0u;
   using namespace gemm;
+  PdlTag pdl_tag(EPI == VB200_EPI_BIAS_RESIDUAL ? 8 : 4);
   // Four tilings, picked by estimated cycles = waves x k-steps x cycles per MMA (tools/mma_bench.cu):
   //   CTA pair 256x256 (~135 cycles per k-step, half as many schedulable units, + ~5 000 cycles per
   //   launch: cluster scheduling, pair TMEM allocation, two cluster-wide syncs — measured with

@@ -392,6 +392,7 @@ static int launch_head_sample(int32_t* x_out, float* loss_out, const void* head_
   const int grid = (items < groups ? items : groups) * 2;
   auto kern = head_sample_kernel<NOISE>;
   VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
+  PdlTag pdl_tag(32);
   VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 2, ta, tb, x_out, loss_out, bias, x_t, row_utt,
                            t_utt, utt, table, n_rows, n_levels, K, d, S, tr, static_cast<uint32_t>(seed),
                            static_cast<uint32_t>(seed >> 32), static_cast<uint32_t>(in_f16 ? 1 : 0)));
