@@ -138,7 +138,7 @@ int pdl_mask() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("VB200_PDL");
-    v = e ? atoi(e) : (4 | 8 | 32);      // default: the one-CTA-per-SM tensor-core kernels (see common.cuh)
+    v = e ? atoi(e) : (2 | 4 | 8 | 16 | 32);      // default: every launch that lands one CTA per SM (see common.cuh)
   }
   return v;
 }

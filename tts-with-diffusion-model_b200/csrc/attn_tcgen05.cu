@@ -556,7 +556,12 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
   if (rc != VB200_OK) return rc;
   dim3 grid((max_T + BQ - 1) / BQ, n_heads, B);
   const float sl2 = scale * 1.4426950408889634f;
-  VB_CONFIGURE_SMEM(flash_attn_kernel, SMEM_BYTES);
+  // A grid that fits the SMs once is padded to one CTA per SM (shared memory only one CTA can hold): launched
+  // early (PDL), two small CTAs would otherwise be packed onto the first SMs that drain.
+  constexpr int SMEM_SOLO = 116 * 1024;
+  const bool solo = static_cast<long long>(grid.x) * grid.y * grid.z <= num_sms();
+  const int smem_bytes = solo ? SMEM_SOLO : SMEM_BYTES;
+  VB_CONFIGURE_SMEM(flash_attn_kernel, SMEM_SOLO);
   {
     static std::atomic<uint64_t> carveout_done{0};                         // per device, like the macro above
     int dev = 0;
@@ -568,8 +573,8 @@ extern "C" int vb200_flash_attn_varlen(void* out_bf16, const void* qkv_bf16, con
       carveout_done.fetch_or(bit, std::memory_order_release);
     }
   }
-  PdlTag pdl_tag(16);
-  VB_CHECK_CUDA(launch_pdl(flash_attn_kernel, grid, dim3(THREADS), SMEM_BYTES, static_cast<cudaStream_t>(stream), 1,
+  PdlTag pdl_tag(solo ? 16 : 64);
+  VB_CHECK_CUDA(launch_pdl(flash_attn_kernel, grid, dim3(THREADS), smem_bytes, static_cast<cudaStream_t>(stream), 1,
                            tm, static_cast<__nv_bfloat16*>(out_bf16), cu_rows, n_heads, sl2, 0.0f));
   VB_CHECK_CUDA(cudaGetLastError());
   return VB200_OK;

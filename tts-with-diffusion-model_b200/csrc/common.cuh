@@ -44,19 +44,24 @@ int head_ce_fused(float* loss_out, const void* head_in, const void* W, const flo
 // that with the "programmatic stream serialization" attribute its CTAs may become resident and run their
 // prologue (barrier init, TMEM allocation, tensor-map prefetch, TMA loads of STATIC data: the first ring of
 // weight tiles) while the previous kernel drains.  Valid under stream capture too.
-// Which launches carry the attribute is a bit mask (VB200_PDL, default 4 | 8 | 32), measured per class on the
-// batch-1 denoise step (88 kernels, one graph replay; tools/latency_ab.py, same box):
+// Which launches carry the attribute is a bit mask (VB200_PDL, default 2 | 4 | 8 | 16 | 32), measured per class on
+// the batch-1 denoise step (88 kernels, one graph replay; tools/latency_ab.py, same box):
 //   4 | 8  GEMMs (QKV / FFN1 behind an AdaLN, the residual GEMMs behind attention / FFN1)   765 -> 735 us,
 //          -> 722 us once the weight halves of the first ring are requested before the wait
 //   32     fused classifier + reverse step                                                   -1.5 us
-//   2      AdaLN                                                                             +17 us
-//   16     attention                                                                         +46 us
+//   AdaLN as it is (eight small blocks per SM)                                               +17 us
+//   attention as it is (two CTAs per SM)                                                     +46 us
 //   1      every launch (what rounds 1 and 2 first measured: 832 against 797 us, "PDL is slower")
 // The difference is CTA placement: an early-launched grid takes SM slots as they free up.  The tensor-core
 // GEMMs fit one CTA per SM, so nothing changes for them but the start time; attention (two CTAs per SM) and
 // AdaLN (eight blocks) get PACKED onto the first SMs that drain instead of being spread breadth-first over
-// idle SMs, and a one-wave launch then runs at half speed.  At 32 utterances per GPU the same mask gives
-// 12.56 -> 12.50 ms per step; at 256 it is neutral.
+// idle SMs, and a one-wave launch then runs at half speed.  Hence, for grids that fit the SMs once, those two
+// kernels ask for 116 KB of dynamic shared memory they do not use — one CTA per SM — and then gain from the
+// early launch like the GEMMs:
+//   2      AdaLN, padded                                                                     721 -> 717 us
+//   16     attention, padded                                                                 721 -> 712 us (both: 708)
+// Larger grids (more than one utterance) keep stream order for these two (measured neutral to slightly
+// negative at 32 utterances); the GEMM mask gives 12.56 -> 12.50 ms per step there, 97.2 -> 96.8 ms at 256.
 // cudaFuncSetAttribute is per DEVICE: each launch site remembers which devices it has configured (a
 // process that drives several GPUs would otherwise launch with the 48 KB default on the second one).
 #define VB_CONFIGURE_SMEM(kern, bytes)                                                                   \
@@ -71,8 +76,10 @@ int head_ce_fused(float* loss_out, const void* head_in, const void* W, const flo
     }                                                                                                    \
   } while (0)
 bool pdl_enabled();
-// VB200_PDL is a bit mask: 1 = every launch; 2 = AdaLN; 4 = GEMMs behind an AdaLN (QKV, FFN1); 8 = residual GEMMs;
-// 16 = attention; 32 = fused classifier + reverse step.  A launch site names its class through PdlTag before calling launch_pdl().
+// VB200_PDL is a bit mask: 1 = every launch; 2 = AdaLN padded to one block per SM; 4 = GEMMs behind an AdaLN (QKV,
+// FFN1); 8 = residual GEMMs; 16 = attention padded to one CTA per SM; 32 = fused classifier + reverse step;
+// 64 / 128 = attention / AdaLN grids larger than the SM count.  A launch site names its class through PdlTag
+// before calling launch_pdl().
 int pdl_mask();
 extern thread_local int g_pdl_tag;
 struct PdlTag {

@@ -363,11 +363,20 @@ extern "C" int vb200_adaln(void* out_bf16, vb200_dtype out_dtype, const float* x
   if (d % 256 == 0 && d <= 1024) {
     // contiguous row ranges per warp; enough warps for ~4 resident blocks per SM.  Small M (one
     // utterance at a time) gets one row per warp: there the kernel is latency-, not bandwidth-bound.
-    PdlTag pdl_tag(2);
     const int total_warps = num_sms() * 4 * 8;
     const int rpw = (M + total_warps - 1) / total_warps;
     const int warps = (M + rpw - 1) / rpw;
     const int grid = (warps + 7) / 8;
+    // one block per SM for a grid that fits the SMs once (see flash_attn: no packing under PDL)
+    constexpr int SMEM_SOLO = 116 * 1024;
+    const bool solo = grid <= num_sms() && d == 1024;
+    PdlTag pdl_tag(solo ? 2 : 128);
+    if (solo) {
+      VB_CONFIGURE_SMEM(adaln_rows_kernel<4>, SMEM_SOLO);
+      VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<4>, dim3(grid), dim3(256), SMEM_SOLO, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c, f16));
+      VB_CHECK_CUDA(cudaGetLastError());
+      return VB200_OK;
+    }
     switch (d / 256) {
       case 1: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<1>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c, f16)); break;
       case 2: VB_CHECK_CUDA(launch_pdl(adaln_rows_kernel<2>, dim3(grid), dim3(256), 0, st, 1, o, x, table, level_utt, row_utt, M, rpw, eps, k, c, f16)); break;
