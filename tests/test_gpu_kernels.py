@@ -49,7 +49,8 @@ def _rand_bf16(shape, seed, scale=1.0):
 
 # ---------------------------------------------------------------- GEMM
 GEMM_SHAPES = [(128, 256, 64), (300, 256, 128), (1027, 3072, 1024), (1027, 1024, 4096),
-               (77, 8200, 256), (4096, 4096, 1024), (1, 64, 64), (257, 72, 200)]
+               (77, 8200, 256), (4096, 4096, 1024), (1, 64, 64), (257, 72, 200),
+               (300, 384, 128), (130, 192, 64)]          # N % 192 == 0, one wave: the 128x192 tiling (16-bit outputs)
 
 
 @pytest.mark.parametrize("simt", [False, True], ids=["tcgen05", "simt"])
@@ -66,8 +67,9 @@ def test_gemm_plain(L, M, N, K, simt):
 
 
 @pytest.mark.parametrize("simt", [False, True], ids=["tcgen05", "simt"])
-def test_gemm_epilogues(L, simt):
-    M, N, K = 515, 1024, 512
+@pytest.mark.parametrize("N", [1024, 768])          # 768: the 128x192 tiling for the 16-bit outputs
+def test_gemm_epilogues(L, simt, N):
+    M, K = 515, 512
     A, W = _rand_bf16((M, K), 3), _rand_bf16((N, K), 4, K ** -0.5)
     bias = torch.randn(N, device=DEV)
     resid = torch.randn(M, N, device=DEV)

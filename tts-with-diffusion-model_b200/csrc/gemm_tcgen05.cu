@@ -40,7 +40,7 @@ template <int CTAS, int BN> struct Cfg {
   static constexpr int B_ROWS = BN / CTAS;
   static constexpr int B_BYTES = B_ROWS * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (4 * 48 * 1024) / STAGE_BYTES;   // 4 x 48 KB, 6 x 32 KB, 8 x 24 KB
+  static constexpr int STAGES = (4 * 48 * 1024) / STAGE_BYTES;   // 4 x 48 KB, 4 x 40 KB (BN = 192), 6 x 32 KB, 8 x 24 KB
 };
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = (2 + EPI_WARPS) * 32;   // 320
@@ -235,7 +235,11 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
     const int sw = lane & 7;                   // SWIZZLE_128B: 16-byte chunk index ^= row % 8
     constexpr bool kWide = sizeof(OutT) == 4;  // fp32: 32 columns per 128-byte row, else 64
     constexpr int CHUNK_COLS = kWide ? 32 : 64;
-    constexpr int CHUNKS = HALF_COLS / CHUNK_COLS;
+    // columns of the tile handled by this half of the epilogue warps: BN / 2 each, except BN = 192 (not a
+    // multiple of 2 x 64): 128 + 64
+    constexpr int HALF0_COLS = BN == 192 ? 128 : HALF_COLS;
+    const int col_base = half * HALF0_COLS;
+    const int n_chunks = (half == 0 ? HALF0_COLS : BN - HALF0_COLS) / CHUNK_COLS;
     const bool epi_leader = elect_one();       // the lane that owns this warp's bulk-store group
     int it = 0;
     for (int tile = tile0; tile < num_tiles; tile += tile_stride, ++it) {
@@ -245,16 +249,16 @@ __global__ void __launch_bounds__(gemm::THREADS, 1) gemm_tcgen05_kernel(
       if (EPI != VB200_EPI_NONE && VB200_GEMM_BIAS_PREFETCH) {
         // this warp's slice of the bias into L1 while the accumulator is still being computed: in a one-tile
         // launch (one utterance) the first __ldg below is otherwise an exposed L2 round trip per GEMM
-        const int nb0 = n_blk * BN + half * HALF_COLS + lane * 32;
-        if (lane * 32 < HALF_COLS && nb0 < N) prefetch_l1(bias + nb0);
+        const int nb0 = n_blk * BN + col_base + lane * 32;
+        if (lane * 32 < n_chunks * CHUNK_COLS && nb0 < N) prefetch_l1(bias + nb0);
       }
       mbar_wait(&acc_full[as], aphase);
       tc_fence_after();
       const int row0 = (m_blk * CTAS + cta_rank) * BM + quad * 32;
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + half * HALF_COLS;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN + col_base;
 #pragma unroll 1
-      for (int c = 0; c < CHUNKS; ++c) {
-        const int n0 = n_blk * BN + half * HALF_COLS + c * CHUNK_COLS;
+      for (int c = 0; c < n_chunks; ++c) {
+        const int n0 = n_blk * BN + col_base + c * CHUNK_COLS;
         if (epi_leader) tma_store_wait_read();  // previous store has finished reading the staging tile
         __syncwarp();
 #pragma unroll
@@ -355,11 +359,16 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, vb200_dtype a_d
   const long t_narrow = N > 128 ? waves(static_cast<long>(mt) * ((N + 127) / 128), sms) * ksteps * 99 : (1l << 60);
   const long t_n64 = (sizeof(OutT) == 4 && N > 64) ? waves(static_cast<long>(mt) * ((N + 63) / 64), sms) * ksteps * 75
                                                    : (1l << 60);
+  // one CTA 128x192 (~130): only as a ONE-wave launch of a bf16 / fp16 output whose N it divides — QKV of one
+  // utterance: 9 x 16 = 144 tiles on 148 SMs, 640 KB of operands per CTA, against 108 tiles of 768 KB
+  const long tiles_192 = static_cast<long>(mt) * (N / 192);
+  const long t_n192 = (sizeof(OutT) == 2 && N % 192 == 0 && tiles_192 <= sms) ? ksteps * 130 : (1l << 60);
   int ctas = t_pair <= t_wide ? 2 : 1;
-  bool narrow = false, narrow64 = false;
+  bool narrow = false, narrow64 = false, n192 = false;
   long best = ctas == 2 ? t_pair : t_wide;
   if (t_narrow < best) { ctas = 1; narrow = true; best = t_narrow; }
   if (t_n64 < best) { ctas = 1; narrow = false; narrow64 = true; best = t_n64; }
+  if (t_n192 < best) { ctas = 1; narrow = false; narrow64 = false; n192 = true; best = t_n192; }
   // VB200_GEMM_TILE=pair|wide|narrow|n64 forces a tiling (A/B measurements, tools/gemm_small_probe.py)
   static int tile_forced = -1;
   if (tile_forced < 0) {
@@ -370,8 +379,9 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, vb200_dtype a_d
     ctas = tile_forced == 1 ? 2 : 1;
     narrow = tile_forced == 3 && N > 128;
     narrow64 = tile_forced == 4 && sizeof(OutT) == 4 && N > 64;
+    n192 = false;
   }
-  const int bn = narrow64 ? 64 : (narrow ? 128 : BN);
+  const int bn = n192 ? 192 : narrow64 ? 64 : (narrow ? 128 : BN);
   CUtensorMap ta, tb, tout;
   int rc = cached_tmap(&ta, a_dt, A, K, M, static_cast<uint64_t>(K) * 2, BK, BM);
   if (rc != VB200_OK) return rc;
@@ -383,7 +393,13 @@ static int launch_gemm(void* out, vb200_dtype dt, const void* A, vb200_dtype a_d
   const int tiles = ((M + BM * ctas - 1) / (BM * ctas)) * ((N + bn - 1) / bn);
   const int groups = num_sms() / ctas;
   const int grid = (tiles < groups ? tiles : groups) * ctas;
-  if (narrow64) {
+  if (n192) {
+    if constexpr (sizeof(OutT) == 2) {
+      auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 192>;
+      VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
+      VB_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(THREADS), SMEM_BYTES, st, 1, ta, tb, tout, bias, M, N, K, a_f16));
+    }
+  } else if (narrow64) {
     if constexpr (sizeof(OutT) == 4) {
       auto kern = gemm_tcgen05_kernel<EPI, OutT, 1, 64>;
       VB_CONFIGURE_SMEM(kern, SMEM_BYTES);
