@@ -142,6 +142,26 @@ def test_attention_last_block_lengths(L, amp):
     assert err.max().item() < (2e-2 if amp == 1.0 else 3e-2 * amp), err.max().item()      # bf16 output ulp grows with |V|
 
 
+def test_attention_output_does_not_depend_on_the_batch(L):
+    """An utterance's attention output is the same bits whether it is launched alone (a one-wave grid: padded to one
+    CTA per SM and launched with PDL) or inside a batch that fills the GPU several times over — what the
+    batch-composition invariance of the generated codes rests on."""
+    heads, d = 2, 128
+    lens = [300, 1027, 17, 131, 64, 200] * 5                 # 30 utterances: 9 x 2 x 30 CTAs
+    M = sum(lens)
+    qkv = _rand_bf16((M, 3 * d), 21)
+    cu = torch.tensor([0] + list(np.cumsum(lens)), dtype=torch.int32, device=DEV)
+    big = torch.empty(M, d, dtype=torch.bfloat16, device=DEV)
+    L.flash_attn_varlen(big, qkv, cu, max(lens), heads, 64 ** -0.5)
+    assert (big.float() - _attn_ref(qkv, lens, heads)).abs().max().item() < 2e-2
+    r0 = 0
+    for T in lens[:6]:                                       # each utterance alone
+        one = torch.empty(T, d, dtype=torch.bfloat16, device=DEV)
+        L.flash_attn_varlen(one, qkv[r0:r0 + T].contiguous(), torch.tensor([0, T], dtype=torch.int32, device=DEV), T, heads, 64 ** -0.5)
+        assert torch.equal(one, big[r0:r0 + T]), T
+        r0 += T
+
+
 # ---------------------------------------------------------------- elementwise
 def test_adaln_layernorm_gather(L):
     from oracle import denoiser as on
