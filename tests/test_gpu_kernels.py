@@ -67,9 +67,9 @@ def test_gemm_plain(L, M, N, K, simt):
 
 
 @pytest.mark.parametrize("simt", [False, True], ids=["tcgen05", "simt"])
-@pytest.mark.parametrize("N", [1024, 768])          # 768: the 128x192 tiling for the 16-bit outputs
-def test_gemm_epilogues(L, simt, N):
-    M, K = 515, 512
+@pytest.mark.parametrize("M,N,K", [(515, 1024, 512), (515, 768, 512),
+                                   (1027, 3072, 256)])     # the last: 144 tiles of 128x192 (16-bit outputs), one wave
+def test_gemm_epilogues(L, simt, M, N, K):
     A, W = _rand_bf16((M, K), 3), _rand_bf16((N, K), 4, K ** -0.5)
     bias = torch.randn(N, device=DEV)
     resid = torch.randn(M, N, device=DEV)
