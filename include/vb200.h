@@ -97,7 +97,10 @@ int vb200_embed_gather(float* x_out, const void* text_w, const void* prom_w, con
 
 /* N1: AdaLN.forward (base.py:145-158): h = LN(x) (no affine, eps); h = c(1-k h)h;
  * y = gamma_l * h + beta_l with table (n_rows, 2d) fp32 = [exp(log gamma) | beta] (exp applied
- * once at weight-pack time).  Row l for utterance b is level_utt[b].  out (M, d) of out_dtype. */
+ * once at weight-pack time).  Row l for utterance b is level_utt[b].  out (M, d) of out_dtype.
+ * `table`, `level_utt` and `row_utt` are read before the kernel waits on its predecessor in the stream
+ * (programmatic dependent launch): they must not be produced by the launch immediately in front of this
+ * one (the engine writes levels / timesteps once per denoise step); `x` has no such restriction. */
 int vb200_adaln(void* out, vb200_dtype out_dtype, const float* x, const float* table, const int32_t* level_utt,
                 const int32_t* row_utt, int32_t M, int32_t d, float eps, float k, float c,
                 vb200_stream_t stream);

@@ -3,6 +3,10 @@
 // One warp per row; 16-byte vector accesses; fp32 math.
 #include "common.cuh"
 
+#ifndef VB200_ADALN_EARLY_PARAMS
+#define VB200_ADALN_EARLY_PARAMS 1
+#endif
+
 namespace vb200 {
 
 __device__ __forceinline__ void add_bf16x8(float (&acc)[8], const __nv_bfloat16* p) {
@@ -235,7 +239,6 @@ __global__ void __launch_bounds__(256) adaln_rows_kernel(
     const int32_t* __restrict__ level_utt, const int32_t* __restrict__ row_utt, int M, int rows_per_warp,
     float eps, float k, float c, int out_f16) {
   pdl_launch_dependents();
-  pdl_wait();                                   // everything below reads / writes activations
   constexpr int d = NV * 256;
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -243,6 +246,16 @@ __global__ void __launch_bounds__(256) adaln_rows_kernel(
   const int r_end = min(r_begin + rows_per_warp, M);
   float g[NV][8], bt[NV][8];
   int cached = -1;
+#if VB200_ADALN_EARLY_PARAMS
+  // The [gamma | beta] row of the first row's level is fetched BEFORE the wait on the previous kernel (row_utt ->
+  // level_utt -> table: three dependent loads): the layout and the levels / timesteps are written once per
+  // denoise step, never by the kernel right in front of an AdaLN.
+  if (r_begin < r_end) {
+    cached = level_utt[row_utt[r_begin]];
+    adaln_load_params<NV>(table, cached, lane, g, bt);
+  }
+#endif
+  pdl_wait();                                   // everything below reads / writes activations
   for (int r = r_begin; r < r_end; ++r) {
     const float* xr = x + static_cast<size_t>(r) * d;
     float v[NV][8];
