@@ -595,3 +595,43 @@ def test_cli_main_end_to_end(tmp_path, monkeypatch):
     assert dec and dec[-1][1] == (1, 8, 20)                 # (b q t): 20 frames x 8 levels went to the decoder
     wr = [c for c in calls if c[0] == "write"]
     assert wr and wr[-1][1] == str(out) and wr[-1][3] == 24_000
+
+
+def test_codes_do_not_depend_on_the_launch_order_mode():
+    """Programmatic dependent launch (default: GEMMs, fused classifier, one-wave attention / AdaLN; loads of weights
+    and AdaLN rows hoisted in front of the wait) only moves WHEN kernels start: the full-size model generates the
+    same codes with it, without it (VB200_PDL=0) and with it on every launch (VB200_PDL=255), for one utterance
+    (every kernel one wave) and for a ragged batch.  The mask is read once per process, hence subprocesses."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    child = r'''
+import sys, hashlib, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import bench
+from vall_e.vall_e.diffusion import Diffusion
+torch.manual_seed(0)
+m = Diffusion(**bench.MODEL, n_steps=7, transition="absorbing")
+for blk in m.blocks:
+    for sub in (blk.attn, blk.ffn):
+        torch.nn.init.normal_(sub.norm.emb.weight, std=0.02)
+m = m.to("cuda")
+h = hashlib.sha256()
+for shapes in ([(50, 225, 750)], [(50, 225, 300), (7, 40, 130), (30, 100, 333)]):
+    utts = [bench.synth_utterance(i, a, b) for i, (a, b, _) in enumerate(shapes)]
+    out = m.generate_audio([u[0].cuda() for u in utts], [u[1].cuda() for u in utts], resp_lens=[c for _, _, c in shapes], seed=9)
+    h.update(torch.cat(out).cpu().numpy().tobytes())
+print("CODES", h.hexdigest())
+''' % (str(root), str(root / "tts-with-diffusion-model_b200"))
+    digests = {}
+    for mask in (None, "0", "255"):
+        env = dict(os.environ)
+        env.pop("VB200_PDL", None)
+        if mask is not None:
+            env["VB200_PDL"] = mask
+        r = subprocess.run([sys.executable, "-c", child], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[mask] = [ln for ln in r.stdout.splitlines() if ln.startswith("CODES")][-1]
+    assert digests[None] == digests["0"] == digests["255"], digests
